@@ -1,0 +1,299 @@
+// Small-sequence multi-head attention on CUDA cores (fp32 math): the parity-mode kernel for the
+// three attention flavours of the towers (S <= 256, head dim 64):
+//   FULL         fusion block   softmax(q k^T / 8) v                     (nn.MultiheadAttention)
+//   TRAJ_CAUSAL  decoder        mask[i,j] = traj[i]==traj[j] && j<=i, computed from traj_index in
+//                               shared memory -- the [N,1,T,T] mask of allenact_dino_transformer.py:399-402
+//                               is never materialised
+//   T5_BIAS      T5 encoder     unscaled scores + relative bias [H,S,S] + key padding mask
+// One CTA per (sequence, head); Q/K/V (and dO) of that head live in shared memory, rows padded to
+// kill bank conflicts.  Forward saves the log-sum-exp per row; backward recomputes P from it.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int DH = 64;
+constexpr int kThreads = 128;  // 4 warps
+constexpr int kMaxS = 256;
+constexpr int kMaxChunks = kMaxS / 32;
+
+template <typename T> struct Pad { static constexpr int v = 1; };
+template <> struct Pad<__nv_bfloat16> { static constexpr int v = 2; };
+
+struct AttnArgs {
+  int mode;
+  const void* q; const void* k; const void* v; long long ld;
+  void* o; const void* d_o; long long ldo;
+  void* dq; void* dk; void* dv; long long ldd;
+  float* lse;
+  const int64_t* traj; const float* bias; const int64_t* keymask;
+  int B, S, H;
+  float scale;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_head(T* dst, const T* src, long long ld, int S, int lds) {
+  // src points at row 0 of this (sequence, head); copy [S, 64] -> dst[S][lds]
+  for (int e = threadIdx.x; e < S * (DH / 4); e += kThreads) {
+    const int r = e / (DH / 4), c = (e % (DH / 4)) * 4;
+    const float4 v = load4<T>(src + (long long)r * ld + c);
+    T* d = dst + r * lds + c;
+    d[0] = from_f<T>(v.x); d[1] = from_f<T>(v.y); d[2] = from_f<T>(v.z); d[3] = from_f<T>(v.w);
+  }
+}
+
+__device__ __forceinline__ bool allowed(const AttnArgs& a, const int* s_traj, const int* s_kmask, int i, int j) {
+  if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) return j <= i && s_traj[i] == s_traj[j];
+  if (a.mode == SVLA_ATTN_T5_BIAS) return s_kmask == nullptr || s_kmask[j] != 0;
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) attn_fwd_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LDS = DH + Pad<T>::v;
+  const int S = a.S, b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  T* sK = reinterpret_cast<T*>(smem_raw);
+  T* sV = sK + S * LDS;
+  float* sQ = reinterpret_cast<float*>(sV + S * LDS);  // [4][64] (2*S*LDS elements: 4-byte aligned)
+  float* sP = sQ + 4 * DH;                                             // [4][S]
+  int* sTraj = reinterpret_cast<int*>(sP + 4 * S);                     // [S] (traj or keymask)
+  const long long row0 = (long long)b * S;
+  const T* gq = reinterpret_cast<const T*>(a.q) + row0 * a.ld + h * DH;
+  load_head<T>(sK, reinterpret_cast<const T*>(a.k) + row0 * a.ld + h * DH, a.ld, S, LDS);
+  load_head<T>(sV, reinterpret_cast<const T*>(a.v) + row0 * a.ld + h * DH, a.ld, S, LDS);
+  if (a.mode == SVLA_ATTN_TRAJ_CAUSAL)
+    for (int i = threadIdx.x; i < S; i += kThreads) sTraj[i] = (int)a.traj[row0 + i];
+  if (a.mode == SVLA_ATTN_T5_BIAS && a.keymask)
+    for (int i = threadIdx.x; i < S; i += kThreads) sTraj[i] = (int)a.keymask[row0 + i];
+  __syncthreads();
+  const int* s_kmask = (a.mode == SVLA_ATTN_T5_BIAS && a.keymask) ? sTraj : nullptr;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nch = (S + 31) / 32;
+  float* myQ = sQ + w * DH;
+  float* myP = sP + w * S;
+  for (int i = w; i < S; i += 4) {
+    __syncwarp();
+    myQ[lane] = to_f<T>(gq[(long long)i * a.ld + lane]);
+    myQ[lane + 32] = to_f<T>(gq[(long long)i * a.ld + lane + 32]);
+    __syncwarp();
+    float sc[kMaxChunks];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      sc[c] = -INFINITY;
+      const int j = c * 32 + lane;
+      if (c < nch && j < S && allowed(a, sTraj, s_kmask, i, j)) {
+        const T* kr = sK + j * LDS;
+        float acc = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < DH; ++d) acc = fmaf(myQ[d], to_f<T>(kr[d]), acc);
+        acc *= a.scale;
+        if (a.mode == SVLA_ATTN_T5_BIAS && a.bias) acc += __ldg(a.bias + ((long long)h * S + i) * S + j);
+        sc[c] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int j = c * 32 + lane;
+      if (c < nch && j < S) {
+        const float p = (sc[c] == -INFINITY) ? 0.f : __expf(sc[c] - mx);
+        myP[j] = p;
+        sum += p;
+      }
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float p = myP[j];
+      o0 = fmaf(p, to_f<T>(sV[j * LDS + lane]), o0);
+      o1 = fmaf(p, to_f<T>(sV[j * LDS + lane + 32]), o1);
+    }
+    T* go = reinterpret_cast<T*>(a.o) + (row0 + i) * a.ldo + h * DH;
+    go[lane] = from_f<T>(o0 * inv);
+    go[lane + 32] = from_f<T>(o1 * inv);
+    if (lane == 0 && a.lse) a.lse[((long long)b * a.H + h) * S + i] = mx + __logf(sum);
+  }
+}
+
+// Backward.  Phase A (key ownership): dK_j, dV_j.  Phase B (query ownership): dQ_i.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LDS = DH + Pad<T>::v;
+  const int S = a.S, b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  T* sQ = reinterpret_cast<T*>(smem_raw);
+  T* sK = sQ + S * LDS;
+  T* sV = sK + S * LDS;
+  T* sdO = sV + S * LDS;
+  float* sLse = reinterpret_cast<float*>(sdO + S * LDS);  // [S]
+  float* sDelta = sLse + S;                                                    // [S]
+  float* sBufA = sDelta + S;                                                   // [4][S]  p column / dS row
+  float* sBufB = sBufA + 4 * S;                                                // [4][S]  dS column
+  int* sTraj = reinterpret_cast<int*>(sBufB + 4 * S);                          // [S]
+  const long long row0 = (long long)b * S;
+  load_head<T>(sQ, reinterpret_cast<const T*>(a.q) + row0 * a.ld + h * DH, a.ld, S, LDS);
+  load_head<T>(sK, reinterpret_cast<const T*>(a.k) + row0 * a.ld + h * DH, a.ld, S, LDS);
+  load_head<T>(sV, reinterpret_cast<const T*>(a.v) + row0 * a.ld + h * DH, a.ld, S, LDS);
+  load_head<T>(sdO, reinterpret_cast<const T*>(a.d_o) + row0 * a.ldo + h * DH, a.ldo, S, LDS);
+  if (a.mode == SVLA_ATTN_TRAJ_CAUSAL)
+    for (int i = threadIdx.x; i < S; i += kThreads) sTraj[i] = (int)a.traj[row0 + i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // delta_i = dO_i . O_i ; lse_i
+  const T* go = reinterpret_cast<const T*>(a.o) + row0 * a.ldo + h * DH;
+  __syncthreads();
+  for (int i = w; i < S; i += 4) {
+    float d = to_f<T>(sdO[i * LDS + lane]) * to_f<T>(go[(long long)i * a.ldo + lane]) +
+              to_f<T>(sdO[i * LDS + lane + 32]) * to_f<T>(go[(long long)i * a.ldo + lane + 32]);
+    d = warp_sum(d);
+    if (lane == 0) {
+      sDelta[i] = d;
+      sLse[i] = a.lse[((long long)b * a.H + h) * S + i];
+    }
+  }
+  __syncthreads();
+  const int nch = (S + 31) / 32;
+  float* colP = sBufA + w * S;
+  float* colDS = sBufB + w * S;
+  // ---- phase A: each warp owns keys j = w, w+4, ...
+  for (int j = w; j < S; j += 4) {
+    __syncwarp();
+    for (int c = 0; c < nch; ++c) {
+      const int i = c * 32 + lane;
+      if (i < S) {
+        float p = 0.f, ds = 0.f;
+        if (allowed(a, sTraj, nullptr, i, j)) {
+          float s = 0.f, dp = 0.f;
+          const T* qr = sQ + i * LDS;
+          const T* dor = sdO + i * LDS;
+          const T* kr = sK + j * LDS;
+          const T* vr = sV + j * LDS;
+#pragma unroll 16
+          for (int d = 0; d < DH; ++d) {
+            s = fmaf(to_f<T>(qr[d]), to_f<T>(kr[d]), s);
+            dp = fmaf(to_f<T>(dor[d]), to_f<T>(vr[d]), dp);
+          }
+          p = __expf(s * a.scale - sLse[i]);
+          ds = p * (dp - sDelta[i]);
+        }
+        colP[i] = p;
+        colDS[i] = ds;
+      }
+    }
+    __syncwarp();
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < S; ++i) {
+      const float p = colP[i], ds = colDS[i];
+      k0 = fmaf(ds, to_f<T>(sQ[i * LDS + lane]), k0);
+      k1 = fmaf(ds, to_f<T>(sQ[i * LDS + lane + 32]), k1);
+      v0 = fmaf(p, to_f<T>(sdO[i * LDS + lane]), v0);
+      v1 = fmaf(p, to_f<T>(sdO[i * LDS + lane + 32]), v1);
+    }
+    T* gdk = reinterpret_cast<T*>(a.dk) + (row0 + j) * a.ldd + h * DH;
+    T* gdv = reinterpret_cast<T*>(a.dv) + (row0 + j) * a.ldd + h * DH;
+    gdk[lane] = from_f<T>(k0 * a.scale);
+    gdk[lane + 32] = from_f<T>(k1 * a.scale);
+    gdv[lane] = from_f<T>(v0);
+    gdv[lane + 32] = from_f<T>(v1);
+  }
+  // ---- phase B: each warp owns queries i = w, w+4, ...
+  float* rowDS = sBufA + w * S;
+  for (int i = w; i < S; i += 4) {
+    __syncwarp();
+    for (int c = 0; c < nch; ++c) {
+      const int j = c * 32 + lane;
+      if (j < S) {
+        float ds = 0.f;
+        if (allowed(a, sTraj, nullptr, i, j)) {
+          float s = 0.f, dp = 0.f;
+          const T* qr = sQ + i * LDS;
+          const T* dor = sdO + i * LDS;
+          const T* kr = sK + j * LDS;
+          const T* vr = sV + j * LDS;
+#pragma unroll 16
+          for (int d = 0; d < DH; ++d) {
+            s = fmaf(to_f<T>(qr[d]), to_f<T>(kr[d]), s);
+            dp = fmaf(to_f<T>(dor[d]), to_f<T>(vr[d]), dp);
+          }
+          ds = __expf(s * a.scale - sLse[i]) * (dp - sDelta[i]);
+        }
+        rowDS[j] = ds;
+      }
+    }
+    __syncwarp();
+    float q0 = 0.f, q1 = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float ds = rowDS[j];
+      q0 = fmaf(ds, to_f<T>(sK[j * LDS + lane]), q0);
+      q1 = fmaf(ds, to_f<T>(sK[j * LDS + lane + 32]), q1);
+    }
+    T* gdq = reinterpret_cast<T*>(a.dq) + (row0 + i) * a.ldd + h * DH;
+    gdq[lane] = from_f<T>(q0 * a.scale);
+    gdq[lane + 32] = from_f<T>(q1 * a.scale);
+  }
+}
+
+template <typename T> size_t fwd_smem(int S) {
+  constexpr int LDS = DH + Pad<T>::v;
+  size_t e = (size_t)2 * S * LDS;
+  return e * sizeof(T) + sizeof(float) * (4 * DH + 4 * S) + sizeof(int) * S + 16;
+}
+template <typename T> size_t bwd_smem(int S) {
+  constexpr int LDS = DH + Pad<T>::v;
+  size_t e = (size_t)4 * S * LDS;
+  return e * sizeof(T) + sizeof(float) * (2 * S + 8 * S) + sizeof(int) * S + 16;
+}
+
+}  // namespace
+
+extern "C" int svla_attn_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                             void* o, long long ldo, int dtype, float* lse, const int64_t* traj, const float* bias,
+                             const int64_t* keymask, int B, int S, int H, int dh, float scale, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && q && k && v && o, "NULL argument");
+  SVLA_CHECK_ARG(dh == DH, "head dim must be 64");
+  SVLA_CHECK_ARG(S >= 1 && S <= kMaxS, "S must be in [1, 256]");
+  SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
+  SVLA_CHECK_ARG(ld % 4 == 0 && ldo % 4 == 0, "leading dims must be multiples of 4");
+  if (B <= 0) return SVLA_OK;
+  AttnArgs a{};
+  a.mode = mode; a.q = q; a.k = k; a.v = v; a.ld = ld; a.o = o; a.ldo = ldo; a.lse = lse;
+  a.traj = traj; a.bias = bias; a.keymask = keymask; a.B = B; a.S = S; a.H = H; a.scale = scale;
+  SVLA_DISPATCH_DTYPE(dtype, T, {
+    const size_t smem = fwd_smem<T>(S);
+    SVLA_CHECK_ARG(smem <= 227 * 1024, "sequence too long for the shared-memory attention kernel at this dtype");
+    SVLA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_fwd_kernel<T><<<B * H, kThreads, smem, as_stream(stream)>>>(a);
+  });
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+extern "C" int svla_attn_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                             const void* o, const void* d_o, long long ldo, void* dq, void* dk, void* dv,
+                             long long ldd, int dtype, const float* lse, const int64_t* traj, int B, int S, int H,
+                             int dh, float scale, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && q && k && v && o && d_o && dq && dk && dv && lse, "NULL argument");
+  SVLA_CHECK_ARG(dh == DH, "head dim must be 64");
+  SVLA_CHECK_ARG(S >= 1 && S <= kMaxS, "S must be in [1, 256]");
+  SVLA_CHECK_ARG(mode == SVLA_ATTN_FULL || mode == SVLA_ATTN_TRAJ_CAUSAL, "backward: FULL or TRAJ_CAUSAL only");
+  SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
+  if (B <= 0) return SVLA_OK;
+  AttnArgs a{};
+  a.mode = mode; a.q = q; a.k = k; a.v = v; a.ld = ld; a.o = const_cast<void*>(o); a.d_o = d_o; a.ldo = ldo;
+  a.dq = dq; a.dk = dk; a.dv = dv; a.ldd = ldd; a.lse = const_cast<float*>(lse); a.traj = traj;
+  a.B = B; a.S = S; a.H = H; a.scale = scale;
+  SVLA_DISPATCH_DTYPE(dtype, T, {
+    const size_t smem = bwd_smem<T>(S);
+    SVLA_CHECK_ARG(smem <= 227 * 1024, "sequence too long for the shared-memory attention backward at this dtype");
+    SVLA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_bwd_kernel<T><<<B * H, kThreads, smem, as_stream(stream)>>>(a);
+  });
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}

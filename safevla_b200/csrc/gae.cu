@@ -1,0 +1,219 @@
+// GAE-lambda over the reward and cost streams in one launch.
+//
+//   delta_t = r_t + gamma * V_{t+1} * m_{t+1} - V_t
+//   g_t     = delta_t + gamma*lam * m_{t+1} * g_{t+1}          (g_T = 0)
+//   ret_t   = g_t + V_t ;  adv_t = ret_t - V_t ;  ret_T = V_T
+//
+// Algorithmic traffic: 20 B read + 16 B written per (t, n) for the stream pair (36 B).
+// Two kernels:
+//   * march: one thread per sampler n walking t = T-1..0, coalesced across n, loads issued
+//     kU steps ahead of the dependent chain.  Same operation order and roundings as the
+//     sequential recursion (explicit _rn intrinsics, no FMA contraction) -> bit-exact.
+//   * warp scan: one warp per sampler, each lane owns a block of consecutive steps; the
+//     recursion is the affine map g -> delta + a*g, composed with a warp suffix scan.
+//     For small N (BASELINE shapes: 64 samplers), where the march has no parallelism.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kU = 8;
+
+struct GaeArgs {
+  const float* r[2];
+  const float* v[2];
+  float* ret[2];
+  float* adv[2];
+  const float* m;
+  int T, N, ns;
+  float gamma, gl;
+};
+
+__global__ void __launch_bounds__(128) gae_march_kernel(GaeArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  const int T = a.T, N = a.N;
+  float g[2] = {0.f, 0.f};
+  for (int s = 0; s < a.ns; ++s) a.ret[s][(size_t)T * N + n] = a.v[s][(size_t)T * N + n];
+  for (int t1 = T; t1 > 0; t1 -= kU) {
+    const int t0 = max(t1 - kU, 0), cnt = t1 - t0;
+    float rr[2][kU], vv[2][kU + 1], mm[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+        mm[j] = __ldg(a.m + off + N);  // m_{t+1}
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) {
+            rr[s][j] = __ldg(a.r[s] + off);
+            vv[s][j] = __ldg(a.v[s] + off);
+          }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (s < a.ns) vv[s][kU] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kU; ++j)  // V_{t+1} of the last step of the chunk
+      if (j == cnt - 1) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) vv[s][j + 1] = __ldg(a.v[s] + (size_t)(t0 + j + 1) * N + n);
+      }
+#pragma unroll
+    for (int j = kU - 1; j >= 0; --j) {
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+        const float m1 = mm[j];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) {
+            const float v0 = vv[s][j], v1 = vv[s][j + 1];
+            const float delta = __fsub_rn(__fadd_rn(rr[s][j], __fmul_rn(__fmul_rn(a.gamma, v1), m1)), v0);
+            g[s] = __fadd_rn(delta, __fmul_rn(__fmul_rn(a.gl, m1), g[s]));
+            const float ret = __fadd_rn(g[s], v0);
+            a.ret[s][off] = ret;
+            a.adv[s][off] = __fsub_rn(ret, v0);
+          }
+      }
+    }
+  }
+}
+
+// warp per sampler; lane owns steps [lane*L, lane*L+L)
+__global__ void __launch_bounds__(128) gae_warp_scan_kernel(GaeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= a.N) return;
+  const int T = a.T, N = a.N;
+  const int L = (T + 31) / 32;
+  const int t0 = min(lane * L, T), t1 = min(t0 + L, T);
+  float A[2] = {1.f, 1.f}, B[2] = {0.f, 0.f};
+  for (int t = t1 - 1; t >= t0; --t) {  // chunk map g_{t1} -> g_{t0} = B + A * g_{t1}
+    const size_t off = (size_t)t * N + n;
+    const float m1 = a.m[off + N], al = a.gl * m1;
+    for (int s = 0; s < a.ns; ++s) {
+      const float delta = a.r[s][off] + a.gamma * a.v[s][off + N] * m1 - a.v[s][off];
+      // apply step t after the already-composed later steps: new(x) = delta + al * (B + A x)
+      B[s] = delta + al * B[s];
+      A[s] = al * A[s];
+    }
+  }
+  // inclusive suffix scan of compositions: F_l = f_l o f_{l+1} o ... o f_31
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float A2 = __shfl_down_sync(0xffffffffu, A[s], o), B2 = __shfl_down_sync(0xffffffffu, B[s], o);
+      if (lane + o < 32) {
+        B[s] = B[s] + A[s] * B2;
+        A[s] = A[s] * A2;
+      }
+    }
+  }
+  float g[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const float nxt = __shfl_down_sync(0xffffffffu, B[s], 1);  // F_{l+1}(0) = g entering lane l's block
+    g[s] = (lane == 31) ? 0.f : nxt;
+  }
+  for (int t = t1 - 1; t >= t0; --t) {
+    const size_t off = (size_t)t * N + n;
+    const float m1 = a.m[off + N], al = a.gl * m1;
+    for (int s = 0; s < a.ns; ++s) {
+      const float v0 = a.v[s][off];
+      const float delta = a.r[s][off] + a.gamma * a.v[s][off + N] * m1 - v0;
+      g[s] = delta + al * g[s];
+      const float ret = g[s] + v0;
+      a.ret[s][off] = ret;
+      a.adv[s][off] = ret - v0;
+    }
+  }
+  if (lane == 0)
+    for (int s = 0; s < a.ns; ++s) a.ret[s][(size_t)T * N + n] = a.v[s][(size_t)T * N + n];
+}
+
+// ---- advantage normalisation --------------------------------------------------------------
+__global__ void __launch_bounds__(256) adv_stats_partial(const float* x, long long n, float* partials) {
+  __shared__ float red[32];
+  float s = 0.f, q = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    s += v;
+    q += v * v;
+  }
+  s = block_sum(s, red);
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 2] = s;
+    partials[blockIdx.x * 2 + 1] = q;
+  }
+}
+__global__ void adv_stats_final(const float* partials, int nb, long long n, float* stats) {
+  __shared__ float red[32];
+  double s = 0.0, q = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nb; ++i) {
+      s += partials[2 * i];
+      q += partials[2 * i + 1];
+    }
+    const double mean = s / (double)n;
+    const double var = n > 1 ? (q - (double)n * mean * mean) / (double)(n - 1) : 0.0;  // torch.std: unbiased
+    stats[0] = (float)mean;
+    stats[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+  }
+  (void)red;
+}
+__global__ void __launch_bounds__(256) adv_normalize(const float* x, float* y, long long n, const float* stats) {
+  const float mean = stats[0], inv = 1.f / (stats[1] + 1e-5f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = (x[i] - mean) * inv;
+}
+
+}  // namespace
+
+extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* costs, const float* value_preds,
+                             const float* c_value_preds, const float* masks, float* returns, float* c_returns,
+                             float* adv, float* c_adv, int T, int N, double gamma, double lam, int algo,
+                             svla_stream stream) {
+  SVLA_CHECK_ARG(ctx, "ctx is NULL");
+  SVLA_CHECK_ARG(T >= 0 && N >= 0, "negative shape");
+  SVLA_CHECK_ARG(rewards && value_preds && masks && returns && adv, "NULL reward-stream buffer");
+  if (N == 0) return SVLA_OK;
+  GaeArgs a;
+  a.r[0] = rewards; a.v[0] = value_preds; a.ret[0] = returns; a.adv[0] = adv;
+  a.r[1] = costs; a.v[1] = c_value_preds; a.ret[1] = c_returns; a.adv[1] = c_adv;
+  a.ns = 1;
+  if (costs) {
+    SVLA_CHECK_ARG(c_value_preds && c_returns && c_adv, "NULL cost-stream buffer");
+    a.ns = 2;
+  }
+  a.m = masks; a.T = T; a.N = N;
+  a.gamma = (float)gamma;
+  a.gl = (float)(gamma * lam);
+  if (algo == 0) algo = (N >= 4096 || T < 16) ? 1 : 2;
+  if (algo == 1) {
+    gae_march_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(a);
+  } else if (algo == 2) {
+    const long long threads = (long long)N * 32;
+    gae_warp_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(a);
+  } else {
+    svla_set_error("svla_gae_dual: bad algo %d", algo);
+    return SVLA_ERR_BAD_ARG;
+  }
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+extern "C" int svla_normalize_advantage(svla_ctx* ctx, const float* adv, float* norm_adv, float* stats,
+                                        long long n, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && adv && norm_adv && stats, "NULL argument");
+  if (n <= 0) return SVLA_OK;
+  int nb = (int)((n + 255) / 256);
+  if (nb > 1024) nb = 1024;
+  adv_stats_partial<<<nb, 256, 0, as_stream(stream)>>>(adv, n, ctx->partials);
+  adv_stats_final<<<1, 32, 0, as_stream(stream)>>>(ctx->partials, nb, n, stats);
+  adv_normalize<<<nb, 256, 0, as_stream(stream)>>>(adv, norm_adv, n, stats);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}

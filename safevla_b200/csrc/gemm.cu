@@ -1,0 +1,30 @@
+// svla_gemm: validation + dispatch between the tcgen05 tensor-core kernel (gemm_tc.cu, bf16 operands)
+// and the fp32-FMA kernel (gemm_simt.cu).
+#include "common.cuh"
+
+int svla_gemm_simt(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st);
+int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st);  // returns SVLA_ERR_BAD_SHAPE if it declines
+bool svla_gemm_tc_supported(const svla_gemm_desc* d);
+
+extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && d, "NULL ctx/desc");
+  SVLA_CHECK_ARG(d->A && d->B && d->C, "NULL operand");
+  SVLA_CHECK_ARG(d->M >= 0 && d->N >= 0 && d->K >= 0, "negative dimension");
+  SVLA_CHECK_ARG(!d->accumulate || d->dtypeC == SVLA_F32, "accumulate needs an fp32 C");
+  SVLA_CHECK_ARG(d->epilogue != SVLA_EPI_RELU_MASK || d->aux, "RELU_MASK needs aux");
+  SVLA_CHECK_ARG(d->lda >= (d->transA ? d->M : d->K), "lda too small");
+  SVLA_CHECK_ARG(d->ldb >= (d->transB ? d->K : d->N), "ldb too small");
+  SVLA_CHECK_ARG(d->ldc >= d->N, "ldc too small");
+  if (d->M == 0 || d->N == 0) return SVLA_OK;
+  const cudaStream_t st = as_stream(stream);
+  if (d->impl == 2) {
+    if (!svla_gemm_tc_supported(d)) {
+      svla_set_error("svla_gemm: impl=tcgen05 requested for an unsupported shape/dtype (M=%d N=%d K=%d)", d->M, d->N,
+                     d->K);
+      return SVLA_ERR_BAD_SHAPE;
+    }
+    return svla_gemm_tc(ctx, d, st);
+  }
+  if (d->impl == 0 && svla_gemm_tc_supported(d)) return svla_gemm_tc(ctx, d, st);
+  return svla_gemm_simt(ctx, d, st);
+}

@@ -1,0 +1,205 @@
+// Fused PPO-Lagrangian loss forward + backward (reference
+// training/online/loss/customized_loss.py:317-449).  One pass over the rollout:
+//   read  A logits + action(8 B) + old_logp, adv, c_adv, values, returns  [+ c_values, c_returns]
+//   write A dlogits + dvalues [+ dcvalues]
+// i.e. 8A + 44 B per (t, n) in the SafePPOLogGrad configuration.  The mean reductions are a
+// deterministic two-stage tree (fixed block partials, last block folds them in a fixed order);
+// the gradient of each mean is closed-form, so no second pass is needed.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;  // rows per tile == threads per block
+constexpr int kMaxA = 64;
+constexpr int kNQ = 10;     // reduced quantities
+
+struct PpoArgs {
+  const float* logits; const int64_t* actions; const float* old_logp; const float* adv; const float* c_adv;
+  const float* values; const float* returns; const float* old_values;
+  const float* c_values; const float* c_returns; const float* old_c_values;
+  const float* lambda_dev;
+  svla_ppo_hparams hp;
+  float* out; float* dlogits; float* dvalues; float* dcvalues;
+  long long R; int A;
+  float* partials; unsigned int* ticket;
+};
+
+// value-loss term: returns 0.5*(.)^2-style contribution and d/dv (un-normalised)
+__device__ __forceinline__ void value_term(float v, float ret, const float* oldp, long long i, float clip,
+                                           int clipped, float& loss, float& dv) {
+  const float e = v - ret;
+  if (!clipped || oldp == nullptr) {
+    loss = 0.5f * e * e;
+    dv = e;
+    return;
+  }
+  const float old = oldp[i];
+  const float d = v - old;
+  const float dc = fminf(fmaxf(d, -clip), clip);
+  const float ec = old + dc - ret;
+  const float l1 = e * e, l2 = ec * ec;
+  const float inside = (d >= -clip && d <= clip) ? 1.f : 0.f;
+  loss = 0.5f * fmaxf(l1, l2);
+  if (l1 > l2) dv = e;
+  else if (l1 < l2) dv = ec * inside;
+  else dv = 0.5f * e + 0.5f * ec * inside;  // torch.max splits ties
+}
+
+__global__ void __launch_bounds__(kRows) ppo_lag_kernel(PpoArgs a) {
+  extern __shared__ float tile[];  // [kRows][A+1]
+  __shared__ float red[32];
+  __shared__ unsigned int s_ticket;
+  const int A = a.A, ldt = A + 1, tid = threadIdx.x;
+  const bool has_pi = a.logits != nullptr, has_v = a.values != nullptr, has_cv = a.c_values != nullptr;
+  const float pen = (a.hp.use_lagrangian && a.lambda_dev) ? *a.lambda_dev : 0.f;
+  const float clip = a.hp.clip_param;
+  const float gs = a.hp.inv_count * a.hp.grad_scale;
+  float acc[kNQ];
+#pragma unroll
+  for (int j = 0; j < kNQ; ++j) acc[j] = 0.f;
+
+  const long long ntiles = (a.R + kRows - 1) / kRows;
+  for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    const long long r0 = tile_i * kRows;
+    const int rows = (int)min((long long)kRows, a.R - r0);
+    const long long i = r0 + tid;
+    const bool live = tid < rows;
+    if (has_pi) {
+      // coalesced load of the [rows, A] logits tile
+      const float* src = a.logits + r0 * A;
+      const int cnt = rows * A;
+      for (int e = tid; e < cnt; e += kRows) tile[(e / A) * ldt + (e % A)] = __ldg(src + e);
+      __syncthreads();
+      if (live) {
+        float* row = tile + tid * ldt;
+        float mx = -INFINITY;
+        for (int k = 0; k < A; ++k) mx = fmaxf(mx, row[k]);
+        float se = 0.f;
+        for (int k = 0; k < A; ++k) se += expf(row[k] - mx);
+        const float lse = mx + logf(se);
+        const int act = (int)a.actions[i];
+        const float logp_a = row[act] - lse;
+        float H = 0.f;
+        for (int k = 0; k < A; ++k) {
+          const float lp = row[k] - lse;
+          const float p = expf(lp);
+          H -= (p > 0.f) ? p * lp : 0.f;
+        }
+        const float oldlp = a.old_logp[i];
+        const float ratio = expf(logp_a - oldlp);
+        const float clamped = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+        const float x = a.adv[i] - (a.c_adv ? pen * a.c_adv[i] : 0.f);
+        const float onep = 1.f + pen;
+        const float surr1 = ratio * x / onep, surr2 = clamped * x / onep;
+        const bool use_clamped = surr2 < surr1;
+        const float aloss = -(use_clamped ? surr2 : surr1);
+        acc[0] += aloss;
+        acc[1] += -H;
+        acc[4] += oldlp - logp_a;
+        acc[5] += (fabsf(ratio - 1.f) > clip) ? 1.f : 0.f;
+        acc[6] += ratio;
+        acc[7] += x / onep;
+        // d total / d logits
+        const float g_lp = use_clamped ? 0.f : -(ratio * x / onep) * a.hp.w_action * gs;
+        const float g_ent = a.hp.w_entropy * gs;
+        for (int k = 0; k < A; ++k) {
+          const float lp = row[k] - lse;
+          const float p = expf(lp);
+          float g = g_lp * ((k == act ? 1.f : 0.f) - p);
+          if (g_ent != 0.f) g += g_ent * ((p > 0.f) ? p * (lp + H) : 0.f);
+          row[k] = g;
+        }
+      }
+      __syncthreads();
+      if (a.dlogits) {
+        float* dst = a.dlogits + r0 * A;
+        const int cnt2 = rows * A;
+        for (int e = tid; e < cnt2; e += kRows) dst[e] = tile[(e / A) * ldt + (e % A)];
+      }
+      __syncthreads();
+    }
+    if (live && has_v) {
+      float l, dv;
+      value_term(a.values[i], a.returns[i], a.old_values, i, clip, a.hp.use_clipped_value_loss, l, dv);
+      acc[2] += l;
+      if (a.dvalues) a.dvalues[i] = dv * a.hp.w_value * gs;
+    }
+    if (live && has_cv) {
+      float l, dv;
+      value_term(a.c_values[i], a.c_returns[i], a.old_c_values, i, clip, a.hp.use_clipped_value_loss, l, dv);
+      acc[3] += l;
+      if (a.dcvalues) a.dcvalues[i] = dv * a.hp.w_cvalue * gs;
+    }
+  }
+  // stage 1: block partials
+#pragma unroll
+  for (int j = 0; j < kNQ; ++j) {
+    const float s = block_sum(acc[j], red);
+    if (tid == 0) a.partials[(size_t)blockIdx.x * 16 + j] = s;
+  }
+  __threadfence();
+  if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  // stage 2: last block folds the partials in a fixed order (deterministic)
+  __threadfence();
+  if (tid < 32) {
+    float tot[kNQ];
+#pragma unroll
+    for (int j = 0; j < kNQ; ++j) {
+      float s = 0.f;
+      for (int b = tid; b < (int)gridDim.x; b += 32) s += a.partials[(size_t)b * 16 + j];
+      tot[j] = warp_sum(s);
+    }
+    if (tid == 0) {
+      const float ic = a.hp.inv_count;
+      const float action = tot[0] * ic, ent = tot[1] * ic, val = tot[2] * ic, cval = tot[3] * ic;
+      a.out[0] = a.hp.w_value * val + a.hp.w_action * action + a.hp.w_entropy * ent + a.hp.w_cvalue * cval;
+      a.out[1] = val;
+      a.out[2] = action;
+      a.out[3] = ent;
+      a.out[4] = cval;
+      a.out[5] = tot[4] * ic;
+      a.out[6] = tot[5] * ic;
+      a.out[7] = tot[6] * ic;
+      a.out[8] = pen;
+      a.out[9] = tot[7];
+      for (int j = 10; j < SVLA_PPO_NSCALARS; ++j) a.out[j] = 0.f;
+      *a.ticket = 0u;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int svla_ppo_lag_fwd_bwd(svla_ctx* ctx, const float* logits, const int64_t* actions, const float* old_logp,
+                                    const float* adv, const float* c_adv, const float* values, const float* returns,
+                                    const float* old_values, const float* c_values, const float* c_returns,
+                                    const float* old_c_values, const float* lambda_dev, const svla_ppo_hparams* hp,
+                                    float* out_scalars, float* dlogits, float* dvalues, float* dcvalues, long long R,
+                                    int A, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && hp && out_scalars, "NULL ctx/hp/out_scalars");
+  SVLA_CHECK_ARG(R > 0, "empty batch");
+  if (logits) {
+    SVLA_CHECK_ARG(A >= 1 && A <= kMaxA, "A must be in [1, 64]");
+    SVLA_CHECK_ARG(actions && old_logp && adv, "policy term needs actions/old_logp/adv");
+    SVLA_CHECK_ARG(!hp->use_lagrangian || (c_adv && lambda_dev), "lagrangian term needs c_adv and lambda");
+  }
+  SVLA_CHECK_ARG(!values || returns, "values without returns");
+  SVLA_CHECK_ARG(!c_values || c_returns, "c_values without c_returns");
+  PpoArgs a;
+  a.logits = logits; a.actions = actions; a.old_logp = old_logp; a.adv = adv; a.c_adv = c_adv;
+  a.values = values; a.returns = returns; a.old_values = old_values;
+  a.c_values = c_values; a.c_returns = c_returns; a.old_c_values = old_c_values;
+  a.lambda_dev = lambda_dev; a.hp = *hp;
+  a.out = out_scalars; a.dlogits = dlogits; a.dvalues = dvalues; a.dcvalues = dcvalues;
+  a.R = R; a.A = logits ? A : 1;
+  a.partials = ctx->partials; a.ticket = ctx->tickets + 0;
+  const long long ntiles = (R + kRows - 1) / kRows;
+  int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8);
+  if (grid > kMaxPartialBlocks) grid = kMaxPartialBlocks;
+  const size_t smem = sizeof(float) * kRows * (a.A + 1);
+  ppo_lag_kernel<<<grid, kRows, smem, as_stream(stream)>>>(a);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}

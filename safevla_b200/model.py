@@ -1,0 +1,354 @@
+"""B200SafeActorCritic: drop-in for SafeDinoLLAMATxNavActorCriticSeparate
+(architecture/models/allenact_transformer_models/separate_actor_critic.py:22-37 on top of
+allenact_dino_transformer.py:47-475): three independent towers (actor / reward critic / cost critic),
+same `forward(observations, memory, prev_actions, masks)` signature, same `state_dict` keys, same
+output struct -- but every FLOP runs in libsafevla_b200 (sm_100a) through the explicit schedule in
+tower.py.  Autograd only sees one opaque node per tower output.
+
+Deliberate, documented differences from the reference (results identical with dropout off):
+  * the frozen T5 encoder runs ONCE per rollout on the de-duplicated prompts and is shared by the
+    three towers (reference: per tower, per row, per forward -- SURVEY.md fact 6);
+  * the last fusion layer only evaluates the CLS row it returns (fact 7);
+  * heads that the separate-tower wrapper discards are not evaluated (fact 4);
+  * dropout is not applied (the parity setting; reference trains with p = 0.1, fact 8).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .misc import CategoricalDistr, Memory, SafeActorCriticOutput
+from .params import D, TOWERS, ParamLayout, T5Layout, init_state_dict, t5_spec, tower_spec
+from .tower import TOK, EncStash, T5Encoder, Tower, TowerWeights
+
+ACTOR, CRITIC, COST = 0, 1, 2
+
+
+class _Node(nn.Module):
+    """Empty container used to reproduce the reference's dotted parameter names."""
+
+
+def default_synthetic_tokenizer(goals: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Synthetic goal codec (safevla_b200.synthetic.encode_goal_ids): blank-separated decimal ids,
+    EOS = 1 appended, right-padded with 0 to the batch longest, mask marks real tokens -- the
+    contract of `self.text_tokenizer(goals, return_tensors="pt", padding=True)` at
+    allenact_dino_transformer.py:600-602.  The real t5-small sentencepiece model is not available
+    offline; pass `tokenizer=` (any callable with this contract) to use it."""
+    rows = [[int(tok) for tok in g.split()] + [1] for g in goals]
+    L = max(len(r) for r in rows)
+    ids = torch.zeros(len(rows), L, dtype=torch.int64)
+    am = torch.zeros(len(rows), L, dtype=torch.int64)
+    for i, r in enumerate(rows):
+        ids[i, : len(r)] = torch.tensor(r, dtype=torch.int64)
+        am[i, : len(r)] = 1
+    return ids, am
+
+
+@dataclass
+class RolloutContext:
+    """Everything derived from the observations alone; shared by towers and update repeats."""
+    T: int
+    N: int
+    L: int
+    vis: List[torch.Tensor]          # per camera [R*84, 384] token-major, activation dtype
+    text_u: torch.Tensor             # [U*L, 512] T5 last_hidden_state of the unique prompts (act dtype)
+    text_idx: torch.Tensor           # int64 [R*L] gather index into text_u rows
+    time_step: torch.Tensor          # int64 [T, N]
+    in_hand: Optional[torch.Tensor]  # int64 [T, N] or None
+    traj_nt: torch.Tensor            # int64 [N, T]
+    perm_tn: torch.Tensor            # int64 [T*N]: row t*N+n <- n*T+t
+    perm_nt: torch.Tensor            # int64 [N*T]: row n*T+t <- t*N+n
+    key: tuple = ()
+
+
+class _TowerOutput(torch.autograd.Function):
+    """Opaque autograd node: forward already ran; backward launches the tower's backward schedule and
+    accumulates straight into the flat gradient arena (parameters' .grad are views of it)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, idx, state, out):
+        ctx.model, ctx.idx, ctx.state = model, idx, state
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, idx, state = ctx.model, ctx.idx, ctx.state
+        g = grad_out.contiguous()
+        model._tower_backward_autograd(idx, state, g)
+        return None, None, None, None, None
+
+
+class B200SafeActorCritic(nn.Module):
+    def __init__(self, num_actions: int, num_cameras: int = 1, *, precision: str = "bf16",
+                 device: Optional[torch.device] = None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 seed: int = 0, tokenizer: Optional[Callable] = None, chunk_rows: int = 1024,
+                 stash_budget_bytes: int = 100 << 30, cls_only_last_layer: bool = True,
+                 goal_sensor_uuid: str = "natural_language_spec", rgb_uuid: str = "rgb_dinov2",
+                 manip_uuid: str = "manipulation_rgb_dinov2", in_hand_uuid: str = "an_object_is_in_hand",
+                 time_step_uuid: str = "time_step", traj_idx_uuid: str = "traj_index", extras: str = "eager",
+                 verify_dedupe: bool = True):
+        super().__init__()
+        assert precision in ("bf16", "fp32")
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200SafeActorCritic needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.A, self.C = num_actions, num_cameras
+        self.precision = precision
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.uu = dict(goal=goal_sensor_uuid, rgb=rgb_uuid, manip=manip_uuid, hand=in_hand_uuid,
+                       time=time_step_uuid, traj=traj_idx_uuid)
+        self.tokenizer = tokenizer or default_synthetic_tokenizer
+        self.chunk_rows, self.stash_budget = chunk_rows, stash_budget_bytes
+        self.extras_mode, self.verify_dedupe = extras, verify_dedupe
+        self.trainable_towers: Tuple[int, ...] = (ACTOR, CRITIC, COST)
+
+        self.layout, self.t5_layout = ParamLayout(num_actions, num_cameras), T5Layout()
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        self.param_arena = torch.zeros(self.layout.total, **f32)
+        self.grad_arena = torch.zeros(self.layout.total, **f32)
+        self.shadow_arena = (torch.zeros(self.layout.total, device=self.dev, dtype=torch.bfloat16)
+                             if precision == "bf16" else None)
+        self.t5_arena = torch.zeros(self.t5_layout.total, **f32)
+        self._register_names()
+        self.load_state_dict(state_dict if state_dict is not None
+                             else init_state_dict(num_actions, num_cameras, seed), strict=True)
+
+        self.t5 = T5Encoder(self.t5_layout, self.t5_arena)
+        self.towers: List[Tower] = []
+        for pre in TOWERS:
+            tw = Tower(TowerWeights(self.layout, pre, self.param_arena, self.grad_arena, self.shadow_arena),
+                       num_actions, num_cameras, self.adt, cls_only_last_layer)
+            tw.div_term = self.get_buffer(pre + "time_encoder.div_term")
+            self.towers.append(tw)
+        self._anchor = torch.zeros(1, device=self.dev, requires_grad=True)
+        self._ctx_cache: Optional[RolloutContext] = None
+        self._tok_cache: Dict[bytes, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.time_step_counter = 0
+        self.train()
+
+    # ------------------------------------------------------------------ naming / state dict
+    def _node(self, path: List[str]) -> nn.Module:
+        m: nn.Module = self
+        for part in path:
+            if part not in m._modules:
+                m.add_module(part, _Node())
+            m = m._modules[part]
+        return m
+
+    def _register_names(self):
+        for pre in TOWERS:
+            for k, shape, _ in tower_spec(self.A, self.C):
+                name = pre + k
+                parts = name.split(".")
+                p = nn.Parameter(self.layout.view(self.param_arena, name), requires_grad=True)
+                p.grad = self.layout.view(self.grad_arena, name)
+                self._node(parts[:-1]).register_parameter(parts[-1], p)
+            self._node((pre + "time_encoder").split(".")).register_buffer(
+                "div_term", torch.zeros(D // 2, device=self.dev))
+            # frozen T5: one arena, exposed under every tower prefix as in the reference state_dict
+            te = pre + "visual_encoder.text_encoder."
+            for k, shape, _ in t5_spec():
+                parts = (te + k).split(".")
+                node = self._node(parts[:-1])
+                if pre == TOWERS[0]:
+                    par = nn.Parameter(self.t5_layout.view(self.t5_arena, k), requires_grad=False)
+                else:
+                    par = self.get_parameter(TOWERS[0] + "visual_encoder.text_encoder." + k)
+                node.register_parameter(parts[-1], par)
+                if k == "shared.weight":
+                    self._node((te + "encoder.embed_tokens").split(".")).register_parameter("weight", par)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        res = super().load_state_dict(state_dict, strict=strict)
+        self.refresh_shadow()
+        return res
+
+    def refresh_shadow(self):
+        """bf16 GEMM-operand copy of the fp32 master weights (refreshed by the fused Adam kernel)."""
+        if self.shadow_arena is not None:
+            ops.cast_bf16(self.param_arena, self.shadow_arena)
+
+    def attach_grads(self):
+        """(Re)point every trainable parameter's .grad at its slice of the gradient arena."""
+        for name, slot in self.layout.slots.items():
+            p = self.get_parameter(name)
+            if p.grad is None or p.grad.data_ptr() != self.grad_arena.data_ptr() + 4 * slot.offset:
+                p.grad = self.layout.view(self.grad_arena, name)
+
+    def set_trainable_towers(self, towers: Sequence[int]):
+        """Which towers will receive a gradient this stage (stage 0: critic + cost critic; stages 1-2:
+        actor + critic -- training/online/dinov2_vits_tsfm_base.py:348-378).  Others skip the stash."""
+        self.trainable_towers = tuple(towers)
+
+    # ------------------------------------------------------------------ allenact ActorCriticModel surface
+    def _recurrent_memory_specification(self):
+        return None
+
+    @property
+    def recurrent_memory_specification(self):
+        return None
+
+    def sampler_select(self, keep: list):
+        return None  # update path holds no per-sampler cache (KV cache belongs to the T=1 rollout path)
+
+    # ------------------------------------------------------------------ observation-side preparation
+    def _decode_rows(self, rows_u8: np.ndarray) -> List[str]:
+        return [r.tobytes().rstrip(b"\x00").decode() for r in rows_u8]
+
+    def prepare(self, observations: Dict[str, torch.Tensor], T: int, N: int) -> RolloutContext:
+        rgb = observations[self.uu["rgb"]]
+        goal = observations[self.uu["goal"]]
+        key = (rgb.data_ptr(), rgb._version, goal.data_ptr(), goal._version, T, N)
+        if self._ctx_cache is not None and self._ctx_cache.key == key:
+            return self._ctx_cache
+        R = T * N
+        dev = self.dev
+
+        def tokens(x):
+            x = x.to(dev, non_blocking=True).reshape(R, 384, TOK).contiguous()
+            assert x.dtype == torch.float32
+            return ops.nchw_to_tokens(x, torch.empty(R * TOK, 384, device=dev, dtype=self.adt))
+
+        vis = [tokens(rgb)]
+        if self.C == 2:
+            vis.append(tokens(observations[self.uu["manip"]]))
+        # ---- prompt de-duplication: hash rows on the device, tokenise + encode unique prompts only
+        g = goal.to(dev, non_blocking=True).reshape(R, -1).contiguous()
+        assert g.dtype == torch.uint8
+        hashes = ops.hash_rows(g)
+        uniq, inverse = torch.unique(hashes, return_inverse=True)  # index bookkeeping, not path arithmetic
+        U = uniq.numel()
+        first = torch.full((U,), R, device=dev, dtype=torch.int64)
+        first.scatter_reduce_(0, inverse, torch.arange(R, device=dev), reduce="amin")
+        if self.verify_dedupe and not bool((g == g[first[inverse]]).all()):
+            raise RuntimeError("goal-byte hash collision: rows with equal hash differ")
+        reps = g[first].cpu().numpy()
+        strs = self._decode_rows(reps)
+        ids, am = self.tokenizer(strs)
+        L = ids.shape[1]
+        text_u = self.t5.forward(ids.to(dev), am.to(dev))  # [U*L, 512] fp32
+        if self.adt != torch.float32:
+            text_u = ops.copy_rows(text_u, torch.empty(U * L, D, device=dev, dtype=self.adt), U * L, D)
+        text_idx = (inverse[:, None] * L + torch.arange(L, device=dev)[None, :]).reshape(-1).contiguous()
+        ar = torch.arange(R, device=dev)
+        perm_tn = ((ar % N) * T + ar // N).contiguous()  # dst row t*N+n reads n*T+t
+        perm_nt = ((ar % T) * N + ar // T).contiguous()
+        traj = observations[self.uu["traj"]].to(dev).reshape(T, N)
+        in_hand = None
+        if self.C == 2:
+            in_hand = observations[self.uu["hand"]].to(dev).reshape(T, N).contiguous()
+        ctx = RolloutContext(T, N, L, vis, text_u, text_idx,
+                             observations[self.uu["time"]].to(dev).reshape(T, N).contiguous(), in_hand,
+                             traj.t().contiguous(), perm_tn, perm_nt, key)
+        self._ctx_cache = ctx
+        return ctx
+
+    # ------------------------------------------------------------------ tower schedules
+    def _chunks(self, R: int):
+        c = max(1, min(self.chunk_rows, R))
+        return [(r0, min(R, r0 + c)) for r0 in range(0, R, c)]
+
+    def _chunk_inputs(self, rc: RolloutContext, r0: int, r1: int):
+        vis = [v[r0 * TOK: r1 * TOK] for v in rc.vis]
+        n = (r1 - r0) * rc.L
+        th = ops.copy_rows(rc.text_u, torch.empty(n, D, device=self.dev, dtype=self.adt), n, D,
+                           idx=rc.text_idx[r0 * rc.L: r1 * rc.L])
+        return vis, th
+
+    def stash_bytes_per_row(self, L: int) -> int:
+        S = 1 + TOK * self.C + L
+        e = 2 if self.adt == torch.bfloat16 else 4
+        full = S * (D * 6 + 3 * D + 2048) * e + S * 40  # x, qkv, ao, s1, x1, hf, s2 + stats
+        pre = (TOK * self.C * 3 + L) * D * e + S * D * e
+        return 3 * full + pre
+
+    def tower_forward(self, idx: int, rc: RolloutContext, prev_actions, masks, *, keep: bool,
+                      want_logits: bool, want_values: bool):
+        """Returns (outputs dict, state for tower_backward or None)."""
+        tw = self.towers[idx]
+        R = rc.T * rc.N
+        obs_embed = torch.empty(R, D, device=self.dev, dtype=self.adt)
+        chunks = self._chunks(R)
+        stash_all = keep and (self.stash_bytes_per_row(rc.L) * R * len(self.trainable_towers) <= self.stash_budget)
+        stashes: List[Optional[EncStash]] = []
+        for (r0, r1) in chunks:
+            vis, th = self._chunk_inputs(rc, r0, r1)
+            cls, st = tw.encoder_fwd(vis, th, rc.L, keep=stash_all)
+            obs_embed[r0:r1].copy_(cls)
+            stashes.append(st)
+        out, dstash = tw.decoder_fwd(obs_embed, prev_actions, masks, rc.in_hand, rc.time_step, rc.traj_nt,
+                                     rc.perm_tn, rc.T, rc.N, want_logits, want_values, keep)
+        state = dict(rc=rc, dec=dstash, enc=stashes, chunks=chunks, prev=prev_actions, masks=masks,
+                     stash_all=stash_all) if keep else None
+        return out, state
+
+    def tower_backward(self, idx: int, state, dlogits, dvalues):
+        tw, rc = self.towers[idx], state["rc"]
+        d_obs = tw.decoder_bwd(dlogits, dvalues, state["dec"], state["prev"], state["masks"], rc.in_hand,
+                               rc.traj_nt, rc.perm_nt, rc.T, rc.N)
+        state["dec"] = None
+        for ci, (r0, r1) in enumerate(state["chunks"]):
+            vis, th = self._chunk_inputs(rc, r0, r1)
+            st = state["enc"][ci]
+            if st is None:  # recompute mode
+                _, st = tw.encoder_fwd(vis, th, rc.L, keep=True)
+            tw.encoder_bwd(d_obs[r0:r1], vis, th, rc.L, st)
+            state["enc"][ci] = None
+
+    def _tower_backward_autograd(self, idx: int, state, grad_out: torch.Tensor):
+        pre = TOWERS[idx]
+        sentinel = self.get_parameter(pre + "decoder.norm.weight")
+        if sentinel.grad is None:  # optimizer.zero_grad(set_to_none=True) happened: arena slice is stale
+            lo, hi = self.layout.tower_range[pre]
+            self.grad_arena[lo:hi].zero_()
+        self.tower_backward(idx, state, grad_out if idx == ACTOR else None, grad_out if idx != ACTOR else None)
+        self.attach_grads()
+
+    # ------------------------------------------------------------------ nn.Module forward (drop-in)
+    def forward(self, observations: Dict[str, torch.Tensor], memory: Optional[Memory], prev_actions: torch.Tensor,
+                masks: torch.Tensor):
+        T, N = prev_actions.shape
+        if T == 1:
+            raise NotImplementedError(
+                "single-step (KV-cache) rollout inference is outside the update path built this round "
+                "(SURVEY.md section 8f-2); run the update-mode forward with T > 1")
+        rc = self.prepare({k: v[:T] for k, v in observations.items()}, T, N)
+        pa = prev_actions.to(self.dev).contiguous()
+        mk = masks.to(self.dev, dtype=torch.float32).reshape(T, N).contiguous()
+        grad = torch.is_grad_enabled()
+        outs = {}
+        for idx in (ACTOR, CRITIC, COST):
+            keep = grad and idx in self.trainable_towers
+            o, state = self.tower_forward(idx, rc, pa, mk, keep=keep, want_logits=(idx == ACTOR),
+                                          want_values=(idx != ACTOR))
+            t = o["logits"] if idx == ACTOR else o["values"]
+            if keep:
+                t = _TowerOutput.apply(self._anchor, self, idx, state, t)
+            outs[idx] = t
+        extras = self._extras(outs[COST])
+        aco = SafeActorCriticOutput(distributions=CategoricalDistr(logits=outs[ACTOR]), values=outs[CRITIC],
+                                    c_values=outs[COST], extras=extras)
+        return aco, memory
+
+    def _extras(self, c_values: torch.Tensor):
+        """Logging extras with the reference's quirks: they describe the COST tower
+        (separate_actor_critic.py:35) and are 1-element CPU tensors (allenact_dino_transformer.py:431-455)."""
+        if self.extras_mode == "off":
+            return {}
+        pre = TOWERS[COST]
+        lo, hi = self.layout.tower_range[pre]
+        buf = torch.empty(4, device=self.dev)
+        ops.sq_norm(self.grad_arena[lo:hi], buf[0:1])
+        wslot, bslot = self.layout.slots[pre + "critic.fc.weight"], self.layout.slots[pre + "critic.fc.bias"]
+        ops.sq_norm(self.param_arena[wslot.offset: wslot.offset + 512], buf[1:2])
+        ops.sq_norm(self.param_arena[bslot.offset: bslot.offset + 4], buf[2:3])  # padded slot: zeros beyond [1]
+        ops.sq_norm(self.grad_arena[wslot.offset: wslot.offset + 512], buf[3:4])
+        host = buf.cpu().sqrt()
+        return {"total_norm": host[0:1].clone(), "weight_norm": host[1:2].clone(), "bias_norm": host[2:3].clone(),
+                "weight_grad_norm": host[3:4].clone(), "stop_grad_values": c_values.detach()}

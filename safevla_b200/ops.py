@@ -1,0 +1,282 @@
+"""Tensor-level wrappers over the C ABI: each function validates shapes, passes raw device
+pointers + the current CUDA stream to libsafevla_b200 and returns/filles torch tensors.
+No function here computes anything with PyTorch ops -- torch only owns the memory."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import BF16, F32, IDENT, RowMap, check, dt, get_ctx, load_library, ptr, stream_ptr
+
+
+def _lib():
+    return load_library()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda, "safevla_b200 ops take CUDA tensors only (no CPU fallback)"
+            assert t.is_contiguous(), "non-contiguous tensor passed to a safevla_b200 op"
+
+
+# ---- scan / elementwise path -------------------------------------------------------------------
+def gae_dual(rewards, costs, value_preds, c_value_preds, masks, gamma: float, lam: float, algo: int = 0,
+             out=None):
+    """rewards/costs [T,N(,1)], value_preds/c_value_preds/masks [T+1,N(,1)] fp32.
+    Returns (returns, c_returns [T+1,...], adv, c_adv [T,...])."""
+    _cuda(rewards, costs, value_preds, c_value_preds, masks)
+    T = rewards.shape[0]
+    N = rewards[0].numel()
+    assert value_preds.shape[0] == T + 1 and masks.shape[0] == T + 1
+    if out is None:
+        returns, adv = torch.empty_like(value_preds), torch.empty_like(rewards)
+        c_returns = torch.empty_like(c_value_preds) if costs is not None else None
+        c_adv = torch.empty_like(costs) if costs is not None else None
+    else:
+        returns, c_returns, adv, c_adv = out
+    check(_lib().svla_gae_dual(get_ctx(), ptr(rewards), ptr(costs), ptr(value_preds), ptr(c_value_preds), ptr(masks),
+                               ptr(returns), ptr(c_returns), ptr(adv), ptr(c_adv), T, N, float(gamma), float(lam),
+                               algo, stream_ptr()), "svla_gae_dual")
+    return returns, c_returns, adv, c_adv
+
+
+def normalize_advantage(adv: torch.Tensor):
+    _cuda(adv)
+    out = torch.empty_like(adv)
+    stats = torch.empty(2, device=adv.device, dtype=torch.float32)
+    check(_lib().svla_normalize_advantage(get_ctx(), ptr(adv), ptr(out), ptr(stats), adv.numel(), stream_ptr()),
+          "svla_normalize_advantage")
+    return out, stats
+
+
+def ppo_lag_fwd_bwd(logits, actions, old_logp, adv, c_adv, values, returns, c_values, c_returns, lambda_dev,
+                    hp: L.PpoHparams, old_values=None, old_c_values=None, want_grads: bool = True):
+    """Returns (scalars[16] device tensor, dlogits, dvalues, dcvalues)."""
+    _cuda(logits, actions, old_logp, adv, c_adv, values, returns, c_values, c_returns, lambda_dev)
+    some = logits if logits is not None else (values if values is not None else c_values)
+    dev = some.device
+    if logits is not None:
+        A = logits.shape[-1]
+        R = logits.numel() // A
+        assert actions.dtype == torch.int64 and actions.numel() == R
+    else:
+        A, R = 1, some.numel()
+    scal = torch.empty(L.PPO_NSCALARS, device=dev, dtype=torch.float32)
+    dlogits = torch.empty_like(logits) if (want_grads and logits is not None) else None
+    dvalues = torch.empty_like(values) if (want_grads and values is not None) else None
+    dcvalues = torch.empty_like(c_values) if (want_grads and c_values is not None) else None
+    check(_lib().svla_ppo_lag_fwd_bwd(get_ctx(), ptr(logits), ptr(actions), ptr(old_logp), ptr(adv), ptr(c_adv),
+                                      ptr(values), ptr(returns), ptr(old_values), ptr(c_values), ptr(c_returns),
+                                      ptr(old_c_values), ptr(lambda_dev), C.byref(hp), ptr(scal), ptr(dlogits),
+                                      ptr(dvalues), ptr(dcvalues), R, A, stream_ptr()), "svla_ppo_lag_fwd_bwd")
+    return scal, dlogits, dvalues, dcvalues
+
+
+def lagrange_update(lambda_dev, state_dev, cost_sum_cnt, cost_limit: float, lr: float, upper_bound: float = -1.0):
+    _cuda(lambda_dev, state_dev, cost_sum_cnt)
+    check(_lib().svla_lagrange_update(get_ctx(), ptr(lambda_dev), ptr(state_dev), ptr(cost_sum_cnt), cost_limit, lr,
+                                      upper_bound, stream_ptr()), "svla_lagrange_update")
+
+
+def sq_norm(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x)
+    assert x.dtype == torch.float32
+    if out is None:
+        out = torch.empty(1, device=x.device, dtype=torch.float32)
+    check(_lib().svla_sq_norm(get_ctx(), ptr(x), x.numel(), ptr(out), stream_ptr()), "svla_sq_norm")
+    return out
+
+
+def clip_adam(p, g, m, v, p_bf16, sq_norm_dev, hp: L.AdamHparams):
+    _cuda(p, g, m, v, p_bf16, sq_norm_dev)
+    check(_lib().svla_clip_adam(get_ctx(), ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), ptr(sq_norm_dev),
+                                C.byref(hp), stream_ptr()), "svla_clip_adam")
+
+
+def scale_by(x: torch.Tensor, scale_dev: torch.Tensor):
+    _cuda(x, scale_dev)
+    assert x.dtype == torch.float32 and scale_dev.dtype == torch.float32
+    check(_lib().svla_scale_by(get_ctx(), ptr(x), x.numel(), ptr(scale_dev), stream_ptr()), "svla_scale_by")
+    return x
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib().svla_cast_bf16(get_ctx(), ptr(x), ptr(out), x.numel(), stream_ptr()), "svla_cast_bf16")
+    return out
+
+
+# ---- dense path --------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, trans_b=True, bias=None,
+         residual=None, aux=None, epilogue=L.EPI_NONE, accumulate=False, alpha=1.0, impl=0,
+         M=None, N=None, K=None, lda=None, ldb=None, ldc=None):
+    """out[M,N] = epi(alpha * op(a) op(b) + bias) [+ residual].  a/b/out are 2-D views whose last
+    dim is contiguous (row stride = leading dimension).  trans_b=True is the nn.Linear layout."""
+    for t in (a, b, out, residual, aux):
+        if t is not None:
+            assert t.is_cuda and t.stride(-1) == 1 and t.dim() == 2
+    lda = a.stride(0) if lda is None else lda
+    ldb = b.stride(0) if ldb is None else ldb
+    ldc = out.stride(0) if ldc is None else ldc
+    if M is None:
+        M = a.shape[1] if trans_a else a.shape[0]
+    if K is None:
+        K = a.shape[0] if trans_a else a.shape[1]
+    if N is None:
+        N = b.shape[0] if trans_b else b.shape[1]
+    kb = b.shape[1] if trans_b else b.shape[0]
+    assert kb == K, f"inner dims differ: {K} vs {kb}"
+    assert out.shape[0] >= M and out.shape[1] >= N
+    d = L.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.transA = ptr(a), lda, int(trans_a)
+    d.B, d.ldb, d.transB = ptr(b), ldb, int(trans_b)
+    d.C, d.ldc = ptr(out), ldc
+    d.dtypeA, d.dtypeB, d.dtypeC = dt(a), dt(b), dt(out)
+    d.bias = ptr(bias)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+    if residual is not None:
+        d.residual, d.ldr, d.dtypeR = ptr(residual), residual.stride(0), dt(residual)
+    if aux is not None:
+        d.aux, d.ldaux, d.dtypeAux = ptr(aux), aux.stride(0), dt(aux)
+    d.epilogue, d.accumulate, d.alpha, d.impl = epilogue, int(accumulate), alpha, impl
+    check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
+    return out
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = True):
+    assert x.dim() == 2 and x.stride(1) == 1
+    check(_lib().svla_colsum(get_ctx(), ptr(x), dt(x), x.shape[0], x.shape[1], x.stride(0), ptr(out),
+                             int(accumulate), stream_ptr()), "svla_colsum")
+
+
+def layernorm_fwd(x, gamma, beta, y, *, res=None, token=None, relu=False, eps=1e-5, ymap=IDENT, mean=None,
+                  rstd=None, rows=None):
+    D = x.shape[-1]
+    rows = x.numel() // D if rows is None else rows
+    check(_lib().svla_layernorm_fwd(get_ctx(), ptr(x), ptr(res), dt(x), ptr(gamma), ptr(beta), ptr(token), int(relu),
+                                    eps, ptr(y), dt(y), ymap, ptr(mean), ptr(rstd), rows, D, stream_ptr()),
+          "svla_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, beta, mean, rstd, dx, dgamma, dbeta, *, res=None, relu=False, dymap=IDENT,
+                  dtoken=None, rows=None):
+    D = x.shape[-1]
+    rows = x.numel() // D if rows is None else rows
+    check(_lib().svla_layernorm_bwd(get_ctx(), ptr(dy), dt(dy), dymap, ptr(x), ptr(res), dt(x), ptr(gamma), ptr(beta),
+                                    int(relu), ptr(mean), ptr(rstd), ptr(dx), dt(dx), ptr(dgamma), ptr(dbeta),
+                                    ptr(dtoken), rows, D, stream_ptr()), "svla_layernorm_bwd")
+    return dx
+
+
+def rmsnorm_fwd(x, w, y, eps, rstd=None):
+    D = x.shape[-1]
+    check(_lib().svla_rmsnorm_fwd(get_ctx(), ptr(x), dt(x), ptr(w), eps, ptr(y), dt(y), ptr(rstd), x.numel() // D, D,
+                                  stream_ptr()), "svla_rmsnorm_fwd")
+    return y
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx, dw, accumulate_dx=False):
+    D = x.shape[-1]
+    check(_lib().svla_rmsnorm_bwd(get_ctx(), ptr(dy), dt(dy), ptr(x), dt(x), ptr(w), ptr(rstd), ptr(dx), dt(dx),
+                                  int(accumulate_dx), ptr(dw), x.numel() // D, D, stream_ptr()), "svla_rmsnorm_bwd")
+    return dx
+
+
+def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bias=None, keymask=None):
+    """q/k/v: 2-D views [B*S, >=H*dh] sharing one row stride (e.g. column slices of a packed qkv buffer)."""
+    assert q.stride(0) == k.stride(0) == v.stride(0) and q.dtype == k.dtype == v.dtype == o.dtype
+    check(_lib().svla_attn_fwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), o.stride(0), dt(q),
+                               ptr(lse), ptr(traj), ptr(bias), ptr(keymask), B, S, H, dh, scale, stream_ptr()),
+          "svla_attn_fwd")
+    return o
+
+
+def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, traj=None):
+    assert q.stride(0) == k.stride(0) == v.stride(0) and dq.stride(0) == dk.stride(0) == dv.stride(0)
+    assert o.stride(0) == d_o.stride(0)
+    check(_lib().svla_attn_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), ptr(d_o), o.stride(0),
+                               ptr(dq), ptr(dk), ptr(dv), dq.stride(0), dt(q), ptr(lse), ptr(traj), B, S, H, dh,
+                               scale, stream_ptr()), "svla_attn_bwd")
+
+
+def attn_cls_fwd(q0, k, v, o, lse, B, S, H=8, dh=64, scale=0.125):
+    assert k.stride(0) == v.stride(0)
+    check(_lib().svla_attn_cls_fwd(get_ctx(), ptr(q0), q0.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), o.stride(0),
+                                   dt(q0), ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_fwd")
+    return o
+
+
+def attn_cls_bwd(q0, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125):
+    assert k.stride(0) == v.stride(0) and dk.stride(0) == dv.stride(0) and o.stride(0) == d_o.stride(0)
+    check(_lib().svla_attn_cls_bwd(get_ctx(), ptr(q0), q0.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), ptr(d_o),
+                                   o.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), dt(q0),
+                                   ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_bwd")
+
+
+def swiglu_fwd(ab, g):
+    F = g.shape[-1]
+    check(_lib().svla_swiglu_fwd(get_ctx(), ptr(ab), ptr(g), dt(ab), g.numel() // F, F, stream_ptr()), "svla_swiglu_fwd")
+    return g
+
+
+def swiglu_bwd(ab, dg, dab):
+    F = dg.shape[-1]
+    check(_lib().svla_swiglu_bwd(get_ctx(), ptr(ab), ptr(dg), ptr(dab), dt(ab), dg.numel() // F, F, stream_ptr()),
+          "svla_swiglu_bwd")
+    return dab
+
+
+def embed_time_fwd(obs_embed, prev_actions, masks, in_hand, time_step, E_a, E_h, div_term, x_out, T, N, A):
+    D = obs_embed.shape[-1]
+    check(_lib().svla_embed_time_fwd(get_ctx(), ptr(obs_embed), dt(obs_embed), ptr(prev_actions), ptr(masks),
+                                     ptr(in_hand), ptr(time_step), ptr(E_a), ptr(E_h), ptr(div_term), ptr(x_out),
+                                     T, N, A, D, stream_ptr()), "svla_embed_time_fwd")
+    return x_out
+
+
+def embed_time_bwd(dx, prev_actions, masks, in_hand, d_obs_embed, dE_a, dE_h, T, N, A):
+    D = dx.shape[-1]
+    check(_lib().svla_embed_time_bwd(get_ctx(), ptr(dx), ptr(prev_actions), ptr(masks), ptr(in_hand),
+                                     ptr(d_obs_embed), dt(d_obs_embed), ptr(dE_a), ptr(dE_h), T, N, A, D,
+                                     stream_ptr()), "svla_embed_time_bwd")
+
+
+def nchw_to_tokens(x: torch.Tensor, out: torch.Tensor):
+    """x [R, C, H, W] fp32 -> out [R, H*W, C]"""
+    R, Cn = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    check(_lib().svla_nchw_to_tokens(get_ctx(), ptr(x), ptr(out), dt(out), R, Cn, P, stream_ptr()),
+          "svla_nchw_to_tokens")
+    return out
+
+
+def copy_rows(src, dst, rows, D, *, lds=None, ldd=None, smap=IDENT, dmap=IDENT, idx=None, accumulate=False):
+    lds = src.stride(-2) if lds is None else lds
+    ldd = dst.stride(-2) if ldd is None else ldd
+    check(_lib().svla_copy_rows(get_ctx(), ptr(src), dt(src), lds, smap, ptr(idx), ptr(dst), dt(dst), ldd, dmap, rows,
+                                D, int(accumulate), stream_ptr()), "svla_copy_rows")
+    return dst
+
+
+def fill_rows(vec, dst, rows, D, *, ldd=None, dmap=IDENT):
+    ldd = dst.stride(-2) if ldd is None else ldd
+    check(_lib().svla_fill_rows(get_ctx(), ptr(vec), ptr(dst), dt(dst), ldd, dmap, rows, D, stream_ptr()),
+          "svla_fill_rows")
+    return dst
+
+
+def hash_rows(rows_u8: torch.Tensor) -> torch.Tensor:
+    assert rows_u8.dtype == torch.uint8 and rows_u8.dim() == 2 and rows_u8.is_contiguous()
+    out = torch.empty(rows_u8.shape[0], device=rows_u8.device, dtype=torch.int64)
+    check(_lib().svla_hash_rows(get_ctx(), ptr(rows_u8), rows_u8.shape[0], rows_u8.shape[1], ptr(out), stream_ptr()),
+          "svla_hash_rows")
+    return out

@@ -73,9 +73,9 @@ def tower_spec(num_actions: int, num_cameras: int) -> List[Tuple[str, Tuple[int,
             (p + "attention.wk.weight", (D, D), "linear"),
             (p + "attention.wv.weight", (D, D), "linear"),
             (p + "attention.wo.weight", (D, D), "linear"),
-            (p + "feed_forward.w1.weight", (DEC_FF, D), "linear"),
-            (p + "feed_forward.w2.weight", (D, DEC_FF), "linear"),
+            (p + "feed_forward.w1.weight", (DEC_FF, D), "linear"),  # w1|w3 adjacent: one fused GEMM
             (p + "feed_forward.w3.weight", (DEC_FF, D), "linear"),
+            (p + "feed_forward.w2.weight", (D, DEC_FF), "linear"),
             (p + "attention_norm.weight", (D,), "ones"),
             (p + "ffn_norm.weight", (D,), "ones"),
         ]

@@ -1,0 +1,170 @@
+"""B200RolloutStorage: device-resident rollout arena with the allenact (fork) RolloutBlockStorage
+surface the reference drives -- `initialize`, `add(observations=, memory=, actions=, action_log_probs=,
+value_preds=, rewards=, costs=, c_value_preds=, masks=)`, `agent_input_for_next_step`, `after_updates`
+(witnessed at architecture/models/allenact_transformer_models/inference_agent.py:172-175,246-269) and,
+per upstream allenact, `before_updates`, `batched_experience_generator`, `to`.
+
+Layout: one contiguous tensor per stream, time-major [T(+1), N, ...] fp32/int64, so GAE reads are
+coalesced across samplers and a `num_mini_batch == 1` batch is a zero-copy view.  GAE for the reward
+and the cost stream is ONE kernel launch (ops.gae_dual).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterator, Optional
+
+import torch
+
+from . import ops
+from .misc import Memory
+
+
+class B200RolloutStorage:
+    def __init__(self, num_steps: int, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200RolloutStorage keeps rollouts in HBM; no CUDA device is visible")
+        self.T = num_steps
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.step = 0
+        self.N = 0
+        self.observations: Dict[str, torch.Tensor] = {}
+        self._initialized = False
+
+    # ------------------------------------------------------------------ allocation
+    def to(self, device):
+        self.dev = torch.device(device)
+        return self
+
+    def initialize(self, *, observations: Dict[str, torch.Tensor], num_samplers: int,
+                   recurrent_memory_specification=None, action_space=None, **kwargs):
+        T, N, dev = self.T, num_samplers, self.dev
+        self.N = N
+        f = dict(device=dev, dtype=torch.float32)
+        self.observations = {k: torch.zeros(T + 1, N, *v.shape[1:], device=dev, dtype=v.dtype)
+                             for k, v in observations.items()}
+        self.rewards = torch.zeros(T, N, 1, **f)
+        self.costs = torch.zeros(T, N, 1, **f)
+        self.value_preds = torch.zeros(T + 1, N, 1, **f)
+        self.c_value_preds = torch.zeros(T + 1, N, 1, **f)
+        self.returns = torch.zeros(T + 1, N, 1, **f)
+        self.c_returns = torch.zeros(T + 1, N, 1, **f)
+        self.adv_targ = torch.zeros(T, N, 1, **f)
+        self.c_adv_targ = torch.zeros(T, N, 1, **f)
+        self.action_log_probs = torch.zeros(T, N, 1, **f)
+        self.actions = torch.zeros(T, N, device=dev, dtype=torch.int64)
+        self.prev_actions = torch.zeros(T + 1, N, device=dev, dtype=torch.int64)
+        self.masks = torch.zeros(T + 1, N, 1, **f)
+        self.episode_cost = torch.zeros(N, **f)
+        self.cost_sum_cnt = torch.zeros(2, **f)  # [sum of finished-episode costs, number of finished episodes]
+        self.norm_adv_targ = None
+        for k, v in observations.items():
+            self.observations[k][0].copy_(v.to(dev), non_blocking=True)
+        self.step = 0
+        self._initialized = True
+
+    # ------------------------------------------------------------------ collection
+    def add(self, *, observations: Dict[str, torch.Tensor], memory: Optional[Memory], actions: torch.Tensor,
+            action_log_probs: torch.Tensor, value_preds: torch.Tensor, rewards: torch.Tensor,
+            costs: Optional[torch.Tensor] = None, c_value_preds: Optional[torch.Tensor] = None,
+            masks: torch.Tensor = None, **kwargs):
+        """One environment step for all samplers (inference_agent.py:255-267 keyword set)."""
+        assert self._initialized and self.step < self.T, "storage full: call after_updates()"
+        t, dev, N = self.step, self.dev, self.N
+        for k, v in observations.items():
+            self.observations[k][t + 1].copy_(v.to(dev).reshape(self.observations[k][t + 1].shape), non_blocking=True)
+        a = actions.to(dev).reshape(N)
+        self.actions[t].copy_(a)
+        self.prev_actions[t + 1].copy_(a)
+        self.action_log_probs[t].copy_(action_log_probs.to(dev).reshape(N, 1))
+        self.value_preds[t].copy_(value_preds.to(dev).reshape(N, 1))
+        self.rewards[t].copy_(rewards.to(dev).reshape(N, 1))
+        if costs is not None:
+            self.costs[t].copy_(costs.to(dev).reshape(N, 1))
+        if c_value_preds is not None:
+            self.c_value_preds[t].copy_(c_value_preds.to(dev).reshape(N, 1))
+        self.masks[t + 1].copy_(masks.to(dev).reshape(N, 1))
+        self.step += 1
+
+    def load_rollout(self, ro: Dict, value_preds, c_value_preds, action_log_probs):
+        """Bulk fill from a synthetic rollout dict (safevla_b200.synthetic.make_rollout): host buffers in,
+        one H2D copy per stream."""
+        dev = self.dev
+        N = ro["actions"].shape[1]
+        first = {k: v[0] for k, v in ro["observations"].items()}
+        if not self._initialized or self.N != N:
+            self.initialize(observations=first, num_samplers=N)
+        for k, v in ro["observations"].items():
+            self.observations[k].copy_(v, non_blocking=True)
+        self.rewards.copy_(ro["rewards"], non_blocking=True)
+        self.costs.copy_(ro["costs"], non_blocking=True)
+        self.masks.copy_(ro["masks"], non_blocking=True)
+        self.actions.copy_(ro["actions"], non_blocking=True)
+        self.prev_actions[1:].copy_(ro["actions"], non_blocking=True)
+        self.prev_actions[0].zero_()
+        self.value_preds.copy_(value_preds.reshape(self.T + 1, N, 1), non_blocking=True)
+        self.c_value_preds.copy_(c_value_preds.reshape(self.T + 1, N, 1), non_blocking=True)
+        self.action_log_probs.copy_(action_log_probs.reshape(self.T, N, 1), non_blocking=True)
+        self.cost_sum_cnt.copy_(torch.stack([ro["episode_cost_sum"], ro["episode_count"]]), non_blocking=True)
+        self.step = self.T
+
+    def h2d_bytes(self) -> int:
+        n = sum(v.numel() * v.element_size() for v in self.observations.values())
+        for t in (self.rewards, self.costs, self.masks, self.actions, self.value_preds, self.c_value_preds,
+                  self.action_log_probs):
+            n += t.numel() * t.element_size()
+        return n
+
+    def agent_input_for_next_step(self) -> Dict:
+        t = self.step
+        return {"observations": {k: v[t:t + 1] for k, v in self.observations.items()}, "memory": None,
+                "prev_actions": self.prev_actions[t:t + 1], "masks": self.masks[t:t + 1]}
+
+    # ------------------------------------------------------------------ update side
+    def before_updates(self, *, next_value: torch.Tensor, next_c_value: Optional[torch.Tensor] = None,
+                       use_gae: bool = True, gamma: float = 0.99, tau: float = 0.95, adv_stats_callback=None,
+                       normalize_advantage: bool = False, gae_algo: int = 0, **kwargs):
+        """Bootstrap + GAE(reward) + GAE(cost) + advantages, one launch."""
+        if not use_gae:
+            raise NotImplementedError("use_gae=False is not used by the shipped config")
+        N = self.N
+        self.value_preds[self.T].copy_(next_value.to(self.dev).reshape(N, 1))
+        if next_c_value is not None:
+            self.c_value_preds[self.T].copy_(next_c_value.to(self.dev).reshape(N, 1))
+        ops.gae_dual(self.rewards, self.costs, self.value_preds, self.c_value_preds, self.masks, gamma, tau, gae_algo,
+                     out=(self.returns, self.c_returns, self.adv_targ, self.c_adv_targ))
+        if normalize_advantage:
+            self.norm_adv_targ, _ = ops.normalize_advantage(self.adv_targ)
+            self.c_norm_adv_targ, _ = ops.normalize_advantage(self.c_adv_targ)
+
+    def batched_experience_generator(self, num_mini_batch: int = 1) -> Iterator[Dict]:
+        T, N = self.T, self.N
+        assert N % num_mini_batch == 0 or num_mini_batch == 1
+        per = N // num_mini_batch
+        for b in range(num_mini_batch):
+            sl = slice(b * per, (b + 1) * per) if num_mini_batch > 1 else slice(0, N)
+            c = (lambda x: x[:, sl].contiguous()) if num_mini_batch > 1 else (lambda x: x)
+            batch = {
+                "observations": {k: c(v[:T]) for k, v in self.observations.items()},
+                "memory": None,
+                "prev_actions": c(self.prev_actions[:T]),
+                "masks": c(self.masks[:T]),
+                "actions": c(self.actions),
+                "old_action_log_probs": c(self.action_log_probs).squeeze(-1),
+                "values": c(self.value_preds[:T]),
+                "c_values": c(self.c_value_preds[:T]),
+                "returns": c(self.returns[:T]),
+                "c_returns": c(self.c_returns[:T]),
+                "adv_targ": c(self.adv_targ),
+                "c_adv_targ": c(self.c_adv_targ),
+            }
+            if self.norm_adv_targ is not None:
+                batch["norm_adv_targ"] = c(self.norm_adv_targ)
+                batch["c_norm_adv_targ"] = c(self.c_norm_adv_targ)
+            yield batch
+
+    def after_updates(self, **kwargs):
+        """Roll the last step into slot 0 for the next rollout."""
+        for v in self.observations.values():
+            v[0].copy_(v[self.T])
+        self.masks[0].copy_(self.masks[self.T])
+        self.prev_actions[0].copy_(self.prev_actions[self.T])
+        self.step = 0

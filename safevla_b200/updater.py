@@ -1,0 +1,159 @@
+"""PPOLagUpdater: the whole constrained-PPO update as one explicit schedule of C-ABI launches.
+
+Replaces the allenact engine's update loop (entered from
+training/online/allenact_trainer.py:47-72 with the hyper-parameters of
+training/online/dinov2_vits_tsfm_base.py:310-379):
+
+    storage full -> GAE(reward) + GAE(cost) ->
+      update_repeats x [ 3-tower forward -> fused PPO-Lagrangian loss fwd+bwd -> tower backwards ->
+                         ONE all-reduce of the flat gradient arena (+ cost scalars in its tail) ->
+                         fused global-norm clip + Adam (+ bf16 shadow refresh, + grad zeroing) ]
+    -> Lagrange-multiplier update on the device.
+
+No autograd, no host sync inside the schedule; scalars for logging are returned as device tensors.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import ops
+from .lagrange import Lagrange
+from .model import ACTOR, COST, CRITIC, B200SafeActorCritic
+from .storage import B200RolloutStorage
+
+
+@dataclass
+class PPOLagConfig:
+    # training/online/dinov2_vits_tsfm_base.py:314-347
+    clip_param: float = 0.1
+    value_loss_coef: float = 0.5
+    entropy_coef: float = 0.0
+    use_clipped_value_loss: bool = False
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    update_repeats: int = 4
+    max_grad_norm: float = 0.5
+    lr: float = 2e-5
+    betas: tuple = (0.9, 0.999)
+    eps: float = 1e-8
+    # stage 0 = ["ppo_value_loss", "safe_ppo_value_loss"]; stage 1 = ["ppo_log_loss"] (:348-378)
+    stage: int = 1
+    # omnisafe Lagrange defaults + README cost limit
+    cost_limit: float = 2.31964
+    lambda_init: float = 0.001
+    lambda_lr: float = 0.035
+    lambda_upper_bound: Optional[float] = None
+    # the reference evaluates all three towers in every forward even when a stage's losses ignore one
+    # (separate_actor_critic.py:27-37); keep that by default so samples/s counts the same work
+    evaluate_unused_towers: bool = True
+
+
+class PPOLagUpdater:
+    TAIL = 64  # floats appended to the gradient arena for the packed scalar all-reduce
+
+    def __init__(self, model: B200SafeActorCritic, cfg: PPOLagConfig = PPOLagConfig(),
+                 process_group: Optional[dist.ProcessGroup] = None):
+        self.model, self.cfg, self.pg = model, cfg, process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = model.dev
+        n = model.layout.total
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self.sq = torch.zeros(1, device=dev)
+        self.adam_step = 0
+        self.tower_steps = [0, 0, 0]
+        self.lagrange = Lagrange(cfg.cost_limit, cfg.lambda_init, cfg.lambda_lr, "Adam", cfg.lambda_upper_bound, dev)
+        # flat [grads | tail] buffer for the single collective; model.grad_arena aliases its head
+        if self.world > 1:
+            self.comm = torch.zeros(n + self.TAIL, device=dev)
+            model.grad_arena = self.comm[:n]
+            for tw in model.towers:
+                tw.W.grads = model.grad_arena
+            model.attach_grads()
+        self.launches = 0
+
+    # ------------------------------------------------------------------
+    def _hp(self, R: int) -> L.PpoHparams:
+        c = self.cfg
+        if c.stage == 0:
+            return L.PpoHparams(c.clip_param, 0.0, 1.0, 0.0, 1.0, 1.0 / R, 1.0, int(c.use_clipped_value_loss), 0)
+        return L.PpoHparams(c.clip_param, 1.0, c.value_loss_coef, c.entropy_coef, 0.0, 1.0 / R, 1.0,
+                            int(c.use_clipped_value_loss), 1)
+
+    def update(self, storage: B200RolloutStorage) -> Dict[str, torch.Tensor]:
+        m, c = self.model, self.cfg
+        T, N = storage.T, storage.N
+        R = T * N
+        storage.before_updates(next_value=storage.value_preds[T], next_c_value=storage.c_value_preds[T],
+                               use_gae=True, gamma=c.gamma, tau=c.gae_lambda)
+        obs = {k: v[:T] for k, v in storage.observations.items()}
+        rc = m.prepare(obs, T, N)
+        pa = storage.prev_actions[:T]
+        mk = storage.masks[:T].view(T, N)
+        grad_towers = (CRITIC, COST) if c.stage == 0 else (ACTOR, CRITIC)
+        m.set_trainable_towers(grad_towers)
+        hp = self._hp(R)
+        scal = None
+        for rep in range(c.update_repeats):
+            outs, states = {}, {}
+            for idx in (ACTOR, CRITIC, COST):
+                if idx not in grad_towers and not c.evaluate_unused_towers:
+                    continue
+                o, st = m.tower_forward(idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR),
+                                        want_values=(idx != ACTOR))
+                outs[idx], states[idx] = o, st
+            if c.stage == 0:
+                scal, _, dv, dcv = ops.ppo_lag_fwd_bwd(
+                    None, None, None, None, None, outs[CRITIC]["values"], storage.returns[:T],
+                    outs[COST]["values"], storage.c_returns[:T], None, hp,
+                    old_values=storage.value_preds[:T], old_c_values=storage.c_value_preds[:T])
+                m.tower_backward(CRITIC, states[CRITIC], None, dv)
+                m.tower_backward(COST, states[COST], None, dcv)
+            else:
+                scal, dl, dv, _ = ops.ppo_lag_fwd_bwd(
+                    outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, storage.adv_targ,
+                    storage.c_adv_targ, outs[CRITIC]["values"], storage.returns[:T], None, None,
+                    self.lagrange.lagrangian_multiplier, hp, old_values=storage.value_preds[:T])
+                m.tower_backward(ACTOR, states[ACTOR], dl, None)
+                m.tower_backward(CRITIC, states[CRITIC], None, dv)
+            del states
+            self._reduce_clip_step(storage, last=(rep == c.update_repeats - 1))
+        # lambda <- proj(lambda + Adam step on (Jc - d)); Jc from the (all-reduced) finished-episode costs
+        cost_pair = self.comm[-self.TAIL:-self.TAIL + 2] if self.world > 1 else storage.cost_sum_cnt
+        self.lagrange.update_from_sum_count(cost_pair)
+        return {"loss_scalars": scal, "lambda": self.lagrange.lagrangian_multiplier, "grad_sq_norm": self.sq}
+
+    def _reduce_clip_step(self, storage: B200RolloutStorage, last: bool):
+        m, c = self.model, self.cfg
+        n = m.layout.total
+        prescale = 1.0
+        if self.world > 1:
+            if last:
+                self.comm[n:n + 2].copy_(storage.cost_sum_cnt)
+            dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)  # the one collective per step
+            prescale = 1.0 / self.world
+        self.adam_step += 1
+        hp = L.AdamHparams(c.lr, c.betas[0], c.betas[1], c.eps, c.max_grad_norm, prescale, self.adam_step, 1)
+        # torch.optim.Adam skips parameters whose .grad is None: only the towers this stage trains are
+        # stepped (they are adjacent in the arena: stage 0 = critic|cost, stages 1-2 = actor|critic)
+        from .params import TOWERS
+        lo = min(m.layout.tower_range[TOWERS[i]][0] for i in m.trainable_towers)
+        hi = max(m.layout.tower_range[TOWERS[i]][1] for i in m.trainable_towers)
+        g = m.grad_arena[lo:hi]
+        if c.max_grad_norm > 0:
+            ops.sq_norm(g, self.sq)
+            if prescale != 1.0:
+                # clip_adam expects the norm of the pre-scaled gradient
+                ops.scale_by(self.sq, torch.full((1,), prescale * prescale, device=m.dev))
+        for i in m.trainable_towers:  # per-parameter Adam step counts start when a tower first trains
+            self.tower_steps[i] += 1
+            hp.step = self.tower_steps[i]
+            a, b = m.layout.tower_range[TOWERS[i]]
+            ops.clip_adam(m.param_arena[a:b], m.grad_arena[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
+                          m.shadow_arena[a:b] if m.shadow_arena is not None else None,
+                          self.sq if c.max_grad_norm > 0 else None, hp)

@@ -1,0 +1,237 @@
+"""CPU suite (no GPU): oracle vs the reference's golden vectors, host logic, and that the C-ABI library
+loads and exports every symbol include/safevla_b200.h declares."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import torch_oracle as TO  # noqa: E402
+from oracle.make_golden import CASES, GOLDEN_DIR, build_inputs  # noqa: E402
+from safevla_b200.params import ParamLayout, T5Layout, init_state_dict, tower_spec  # noqa: E402
+from safevla_b200.synthetic import RolloutSpec, make_rollout, prev_actions_from  # noqa: E402
+
+
+def relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------ oracle pinned on the reference's outputs
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_reference_golden(name):
+    torch.set_num_threads(os.cpu_count() or 1)
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    case = gold["case"]
+    T, N, A, C = case["T"], case["N"], case["A"], case["C"]
+    sd = init_state_dict(A, C, case["wseed"], actor_gain=1.0)
+    spec, ro, extra = build_inputs(case)
+    obs = {k: v[:-1] for k, v in ro["observations"].items()}
+    prev, masks = prev_actions_from(ro["actions"]), ro["masks"][:-1]
+    leaf = {k: (v.clone().requires_grad_(True) if "text_encoder" not in k and not k.endswith("div_term") else v)
+            for k, v in sd.items()}
+    out = TO.safe_model_forward(leaf, obs, prev, masks, A, C)
+    assert relerr(out["logits"], gold["logits"]) < 2e-5
+    assert relerr(torch.log_softmax(out["logits"], -1), gold["log_probs"]) < 2e-5
+    assert relerr(out["values"], gold["values"]) < 2e-5 and relerr(out["c_values"], gold["c_values"]) < 2e-5
+    ret, adv = TO.gae_returns(ro["rewards"], extra["value_preds"], ro["masks"], 0.99, 0.95)
+    cret, cadv = TO.gae_returns(ro["costs"], extra["c_value_preds"], ro["masks"], 0.99, 0.95)
+    out["logits"].retain_grad()
+    total, info = TO.safe_ppo_log_grad(out["logits"], ro["actions"], gold["old_logp"], adv, cadv, out["values"],
+                                       ret[:-1], case["lam"], entropy_coef=0.01)
+    assert abs(total.item() - gold["loss_total"].item()) < 1e-5 * max(1, abs(gold["loss_total"].item()))
+    for k in ("value", "action", "entropy"):
+        assert abs(info[k].item() - gold["info"][k]) < 1e-5 * max(1, abs(gold["info"][k]))
+    total.backward()
+    assert relerr(out["logits"].grad, gold["dlogits"]) < 1e-4
+    for k, gn in gold["grad_norms"].items():
+        g = leaf[k].grad
+        if gn is None:
+            assert g is None or g.abs().max() == 0
+        else:
+            assert abs(g.norm().item() - gn) / max(gn, 1e-8) < 1e-3, k
+    for k, gref in gold["grads"].items():
+        assert relerr(leaf[k].grad, gref) < 1e-3, k
+    # lambda = 0 reduces SafePPOLogGrad to PPOLogGrad (reference KAT)
+    t0, _ = TO.safe_ppo_log_grad(out["logits"].detach(), ro["actions"], gold["old_logp"], adv, cadv,
+                                 out["values"].detach(), ret[:-1], 0.0, entropy_coef=0.01)
+    assert abs(t0.item() - gold["loss_lambda0"].item()) < 1e-5 * max(1, abs(t0.item()))
+
+
+def test_oracle_matches_reference_live():
+    """Runs the unmodified reference (only where /root/reference exists, i.e. the build container)."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present on this box")
+    torch.set_num_threads(os.cpu_count() or 1)
+    A, C, T, N = 6, 1, 5, 2
+    sd = init_state_dict(A, C, 31, actor_gain=1.0)
+    model = ref_shim.build_reference_model(A, C, seed=0, num_samplers=N)
+    model.load_state_dict(sd, strict=True)
+    ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.3, seed=9))
+    obs = {k: v[:-1] for k, v in ro["observations"].items()}
+    prev, masks = prev_actions_from(ro["actions"]), ro["masks"][:-1]
+    with torch.no_grad():
+        ref, _ = model(obs, None, prev, masks)
+        mine = TO.safe_model_forward(sd, obs, prev, masks, A, C)
+    assert relerr(torch.log_softmax(mine["logits"], -1), ref.distributions.logits) < 2e-5
+    assert relerr(mine["values"], ref.values) < 2e-5 and relerr(mine["c_values"], ref.c_values) < 2e-5
+    # KAT (iv): perturbing a finished trajectory leaves later steps / other samplers untouched
+    assert torch.equal(ref.extras["stop_grad_values"], ref.c_values)
+
+
+# ------------------------------------------------------------------ restated pieces: closed forms / KATs
+def test_gae_closed_form_and_masks():
+    T, N = 30, 3
+    r, z, m = torch.ones(T, N, 1), torch.zeros(T + 1, N, 1), torch.ones(T + 1, N, 1)
+    ret, adv = TO.gae_returns(r, z, m, 0.99, 0.95)
+    gl = 0.99 * 0.95
+    assert torch.allclose(ret[:T, 0, 0], torch.tensor([(1 - gl ** (T - t)) / (1 - gl) for t in range(T)]), rtol=1e-5)
+    m[7] = 0
+    ret2, _ = TO.gae_returns(r, z, m, 0.99, 0.95)
+    assert torch.allclose(ret2[6], torch.ones(N, 1))
+    # permuting samplers permutes outputs
+    g = torch.Generator().manual_seed(0)
+    r, v = torch.randn(T, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g)
+    perm = torch.tensor([2, 0, 1])
+    a, _ = TO.gae_returns(r, v, m, 0.99, 0.95)
+    b, _ = TO.gae_returns(r[:, perm], v[:, perm], m[:, perm], 0.99, 0.95)
+    assert torch.equal(a[:, perm], b)
+
+
+def test_lagrange_first_step_is_sign_only():
+    for jc, sign in ((10.0, +1), (0.0, -1)):
+        lag = TO.LagrangeOracle(2.0, init=0.5, lr=0.035)
+        assert abs(lag.update(jc) - (0.5 + sign * 0.035)) < 1e-7
+    lag = TO.LagrangeOracle(2.0, init=0.01)
+    assert lag.update(0.0) == 0.0  # projection onto [0, inf)
+
+
+def test_adam_and_clip_oracle_match_torch():
+    g = torch.Generator().manual_seed(1)
+    p0, gr = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-5)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in (1, 2, 3):
+        ref.grad = gr.clone() * step
+        torch.nn.utils.clip_grad_norm_([ref], 0.5)
+        opt.step()
+        (gc,), _ = TO.clip_grad_norm([gr * step], 0.5)
+        p, m, v = TO.adam_step(p, gc, m, v, step)
+    assert (p - ref.detach()).abs().max() < 1e-7
+
+
+def test_t5_buckets_match_oracle():
+    from safevla_b200.t5_buckets import relative_position_bucket
+    for L in (1, 5, 32, 200):
+        pos = torch.arange(L)
+        assert torch.equal(relative_position_bucket(L), TO.t5_relative_position_bucket(pos[None, :] - pos[:, None]))
+
+
+# ------------------------------------------------------------------ host logic
+def test_param_layout_and_state_dict_contract():
+    for A, C, n_keys in ((6, 1, 411), (20, 2, 417)):
+        sd = init_state_dict(A, C, 0)
+        assert len(sd) == n_keys  # 414 / 417 entries (411 = 414 - the 3 in-hand tables at C=1)
+        lay = ParamLayout(A, C)
+        offs = [(s.offset, s.numel) for s in lay.slots.values()]
+        assert all(o % 64 == 0 for o, _ in offs)
+        assert all(offs[i][0] + offs[i][1] <= offs[i + 1][0] for i in range(len(offs) - 1))
+        n_train = sum(s.numel for s in lay.slots.values())
+        assert n_train == sum(v.numel() for k, v in sd.items() if "text_encoder" not in k and "div_term" not in k)
+        # fused-GEMM adjacency the tower relies on
+        for pre in ("", "critic_tsfm.", "c_critic_tsfm."):
+            for i in range(3):
+                q, k_, v_ = [lay.slots[pre + f"decoder.layers.{i}.attention.w{x}.weight"] for x in "qkv"]
+                assert k_.offset == q.offset + q.numel and v_.offset == k_.offset + k_.numel
+                w1, w3 = [lay.slots[pre + f"decoder.layers.{i}.feed_forward.w{x}.weight"] for x in "13"]
+                assert w3.offset == w1.offset + w1.numel
+    assert 62_000_000 < ParamLayout(6, 1).total < 63_500_000
+    t5 = T5Layout()
+    q, k_ = t5.slots["encoder.block.3.layer.0.SelfAttention.q.weight"], t5.slots["encoder.block.3.layer.0.SelfAttention.k.weight"]
+    assert k_.offset == q.offset + q.numel
+
+
+def test_synthetic_rollout_contract_and_determinism():
+    spec = RolloutSpec(16, 3, 20, 2, episode_end_prob=0.2, seed=5)
+    a, b = make_rollout(spec), make_rollout(spec)
+    o = a["observations"]
+    assert o["rgb_dinov2"].shape == (17, 3, 384, 7, 12) and o["rgb_dinov2"].dtype == torch.float32
+    assert o["natural_language_spec"].shape == (17, 3, 1000) and o["natural_language_spec"].dtype == torch.uint8
+    assert o["time_step"].dtype == torch.int64 and o["traj_index"].dtype == torch.int64
+    assert o["an_object_is_in_hand"].shape == (17, 3, 1)
+    assert all(torch.equal(a["observations"][k], b["observations"][k]) for k in o)
+    assert torch.equal(a["rewards"], b["rewards"]) and torch.equal(a["actions"], b["actions"])
+    # episode boundary <=> mask 0 <=> time_step reset and traj_index bump
+    m = a["masks"][1:, :, 0] == 0
+    assert torch.all(o["time_step"][1:][m] == 0)
+    assert torch.all((o["traj_index"][1:] - o["traj_index"][:-1])[m] % 2048 == 1)
+    ids, am = TO.decode_goal_ids(o["natural_language_spec"][0])
+    assert ids.shape == (3, 32) and am.all() and (ids[:, -1] == 1).all()
+    from safevla_b200.model import default_synthetic_tokenizer
+    s = [r.numpy().tobytes().rstrip(b"\x00").decode() for r in o["natural_language_spec"][0]]
+    ids2, am2 = default_synthetic_tokenizer(s)
+    assert torch.equal(ids, ids2) and torch.equal(am, am2)
+
+
+def test_loss_plugin_constructors_match_reference_signatures():
+    from safevla_b200.losses import PPOLogGrad, PPOValue, SafePPOLogGrad, SafePPOValue
+    cfg = dict(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.0, use_clipped_value_loss=False,
+               action_loss_schedule=None, discrete_critics=False, normalize_advantage=False)  # dinov2_vits_tsfm_base.py:314-322
+    s = SafePPOLogGrad(**cfg)
+    assert s.adv_key == "adv_targ" and s.c_adv_key == "c_adv_targ" and s.action_loss_schedule(123) == 1.0
+    assert PPOLogGrad(**dict(cfg, normalize_advantage=True)).adv_key == "norm_adv_targ"
+    PPOValue(clip_param=0.1, use_clipped_value_loss=False)
+    SafePPOValue(clip_param=0.1, use_clipped_value_loss=False)
+
+
+def test_no_cpu_fallback():
+    """Product entry points must fail loudly without a GPU instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from safevla_b200 import _lib
+    from safevla_b200.model import B200SafeActorCritic
+    from safevla_b200.storage import B200RolloutStorage
+    with pytest.raises(RuntimeError):
+        _lib.get_ctx()
+    with pytest.raises(RuntimeError):
+        B200SafeActorCritic(6, 1)
+    with pytest.raises(RuntimeError):
+        B200RolloutStorage(16)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "safevla_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+# ------------------------------------------------------------------ the C-ABI library
+def test_library_exports_every_declared_symbol():
+    from safevla_b200 import _lib
+    lib = _lib.load_library()
+    header = open(os.path.join(ROOT, "include", "safevla_b200.h")).read()
+    declared = set(re.findall(r"\b(svla_[a-z0-9_]+)\s*\(", header))
+    declared -= {"svla_ctx", "svla_stream"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.PROTOTYPES, f"{name} has no ctypes prototype"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (svla_[a-z0-9_]+)", out))
+    assert declared <= exported
+    assert lib.svla_version() == 100
+    assert b"" == lib.svla_last_error() or isinstance(lib.svla_last_error(), bytes)
+
+
+def test_library_is_sm100a_native():
+    from safevla_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:500]

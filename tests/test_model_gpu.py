@@ -1,0 +1,155 @@
+"""End-to-end parity of the CUDA three-tower model / loss / update against the reference's golden
+vectors (tests/golden/*.pt, minted by oracle/make_golden.py from the unmodified reference code)
+and against the CPU oracle on fresh seeds.  B200 only."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_oracle as TO  # noqa: E402  (checker only)
+from oracle.make_golden import CASES, GOLDEN_DIR, build_inputs  # noqa: E402
+from safevla_b200.params import init_state_dict  # noqa: E402
+from safevla_b200.synthetic import prev_actions_from  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    return ((a.double().cpu() - b.double().cpu()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+
+
+def _setup(name, dev, precision, **kw):
+    from safevla_b200.model import B200SafeActorCritic
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    case = gold["case"]
+    sd = init_state_dict(case["A"], case["C"], case["wseed"], actor_gain=1.0)
+    model = B200SafeActorCritic(case["A"], case["C"], precision=precision, state_dict=sd, device=dev, **kw)
+    spec, ro, extra = build_inputs(case)
+    obs = {k: v[:-1].to(dev) for k, v in ro["observations"].items()}
+    return gold, case, model, ro, extra, obs
+
+
+def _batch(gold, ro, extra, dev):
+    ret, adv = TO.gae_returns(ro["rewards"], extra["value_preds"], ro["masks"], 0.99, 0.95)
+    cret, cadv = TO.gae_returns(ro["costs"], extra["c_value_preds"], ro["masks"], 0.99, 0.95)
+    return {"actions": ro["actions"].to(dev), "old_action_log_probs": gold["old_logp"].to(dev),
+            "adv_targ": adv.to(dev), "c_adv_targ": cadv.to(dev), "values": extra["value_preds"][:-1].to(dev),
+            "returns": ret[:-1].to(dev), "c_returns": cret[:-1].to(dev),
+            "c_values": extra["c_value_preds"][:-1].to(dev)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("cls_only", [True, False])
+def test_golden_forward_loss_backward_fp32(dev, name, cls_only):
+    """BASELINE gate: logits / losses within 1e-4 relative of the reference PyTorch path (fp32)."""
+    from safevla_b200.losses import SafePPOLogGrad
+    gold, case, model, ro, extra, obs = _setup(name, dev, "fp32", cls_only_last_layer=cls_only)
+    out, _ = model(obs, None, prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev))
+    assert relerr(out.distributions.raw_logits, gold["logits"]) < 1e-4
+    assert relerr(out.distributions.logits, gold["log_probs"]) < 1e-4
+    assert relerr(out.values, gold["values"]) < 1e-4
+    assert relerr(out.c_values, gold["c_values"]) < 1e-4
+    loss = SafePPOLogGrad(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.01, use_clipped_value_loss=False,
+                          action_loss_schedule=None, discrete_critics=False, normalize_advantage=False)
+    batch = _batch(gold, ro, extra, dev)
+    total, info = loss.loss(0, batch, out, lagrangian_multiplier=torch.tensor(case["lam"]))
+    for k in ("ppo_total", "value", "action", "entropy"):
+        assert abs(info[k] - gold["info"][k]) <= 1e-4 * max(1.0, abs(gold["info"][k])), (k, info[k], gold["info"][k])
+    assert set(gold["info"]) <= set(info)  # same info-dict keys as the reference
+    total.backward()
+    worst = ("", 0.0)
+    for k, gn in gold["grad_norms"].items():
+        p = model.get_parameter(k)
+        if gn is None:  # reference leaves these without a gradient (cost tower, unused heads)
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+            continue
+        mine = p.grad.norm().item()
+        err = abs(mine - gn) / max(gn, 1e-8)
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < 2e-3, worst
+    for k, gref in gold["grads"].items():
+        assert relerr(model.get_parameter(k).grad, gref) < 2e-3, k
+
+
+def test_golden_stage0_value_losses(dev):
+    from safevla_b200.losses import PPOValue, SafePPOValue
+    name = "cfg1_T16_N1_A6_C1"
+    gold, case, model, ro, extra, obs = _setup(name, dev, "fp32")
+    model.set_trainable_towers((1, 2))
+    out, _ = model(obs, None, prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev))
+    batch = _batch(gold, ro, extra, dev)
+    l1, _ = PPOValue(clip_param=0.1, use_clipped_value_loss=False).loss(0, batch, out)
+    l2, _ = SafePPOValue(clip_param=0.1, use_clipped_value_loss=False).loss(0, batch, out)
+    total = l1 + l2
+    assert abs(total.item() - gold["stage0_loss"].item()) < 1e-4 * gold["stage0_loss"].item()
+    total.backward()
+    for k, gn in gold["stage0_grad_norms"].items():
+        p = model.get_parameter(k)
+        if gn is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+        else:
+            assert abs(p.grad.norm().item() - gn) / max(gn, 1e-8) < 2e-3, k
+
+
+def test_golden_bf16_mode(dev):
+    """bf16 tensor-core mode: same path, looser tolerance (bf16 operands, fp32 accumulation)."""
+    gold, case, model, ro, extra, obs = _setup("cfg1_T16_N1_A6_C1", dev, "bf16")
+    with torch.no_grad():
+        out, _ = model(obs, None, prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev))
+    assert relerr(out.distributions.raw_logits, gold["logits"]) < 5e-2
+    assert relerr(out.values, gold["values"]) < 5e-2
+
+
+def test_chunking_and_recompute_are_exact(dev):
+    """Row-chunked + recompute-in-backward schedules reproduce the single-chunk stash schedule."""
+    from safevla_b200.losses import SafePPOLogGrad
+    name = "T12_N2_A20_C2"
+    grads = []
+    for kw in (dict(chunk_rows=1024), dict(chunk_rows=5), dict(chunk_rows=7, stash_budget_bytes=0)):
+        gold, case, model, ro, extra, obs = _setup(name, dev, "fp32", **kw)
+        out, _ = model(obs, None, prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev))
+        loss = SafePPOLogGrad(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.01, use_clipped_value_loss=False,
+                              action_loss_schedule=None, discrete_critics=False, normalize_advantage=False)
+        total, _ = loss.loss(0, _batch(gold, ro, extra, dev), out, lagrangian_multiplier=torch.tensor(case["lam"]))
+        total.backward()
+        grads.append(model.grad_arena.clone())
+    assert relerr(grads[1], grads[0]) < 1e-5 and relerr(grads[2], grads[0]) < 1e-5
+
+
+def test_updater_matches_oracle_update(dev):
+    """Whole update (GAE -> repeats x [fwd, loss, bwd, clip, Adam] -> lambda) vs the CPU oracle."""
+    from oracle.update_oracle import oracle_update
+    from safevla_b200.model import B200SafeActorCritic
+    from safevla_b200.storage import B200RolloutStorage
+    from safevla_b200.synthetic import RolloutSpec, make_rollout
+    from safevla_b200.updater import PPOLagConfig, PPOLagUpdater
+    T, N, A, C = 8, 2, 6, 1
+    sd = init_state_dict(A, C, seed=21, actor_gain=1.0)
+    ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.2, seed=77))
+    g = torch.Generator().manual_seed(5)
+    vp, cvp = torch.randn(T + 1, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g).abs()
+    logp = -1.7 + 0.1 * torch.randn(T, N, generator=g)
+    cfg = PPOLagConfig(update_repeats=2, lr=1e-3)
+    ref_sd, ref_lam, ref_info = oracle_update(sd, ro, vp, cvp, logp, cfg, A, C)
+    model = B200SafeActorCritic(A, C, precision="fp32", state_dict=sd, device=dev)
+    st = B200RolloutStorage(T, dev)
+    st.load_rollout(ro, vp, cvp, logp)
+    upd = PPOLagUpdater(model, cfg)
+    res = upd.update(st)
+    assert abs(res["lambda"].item() - ref_lam) < 1e-5
+    assert abs(res["loss_scalars"][0].item() - ref_info["last_total"]) < 1e-3 * max(1, abs(ref_info["last_total"]))
+    mine = model.state_dict()
+    worst = 0.0
+    for k, v in ref_sd.items():
+        if "text_encoder" in k:
+            continue
+        worst = max(worst, (mine[k].cpu() - v).abs().max().item())
+    assert worst < 5e-5, worst  # two Adam steps of lr 1e-3: parameters move by ~2e-3
