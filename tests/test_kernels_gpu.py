@@ -180,7 +180,7 @@ def test_sq_norm_and_clip_adam(dev, n):
         hp = L.AdamHparams(2e-5, 0.9, 0.999, 1e-8, 0.5, 1.0, step, 1)
         _ops().clip_adam(p, grad, m, v, shadow, sq, hp)
         assert grad.abs().max().item() == 0.0  # fused zero_grad
-    assert (p - ref.detach()).abs().max().item() < 2e-7
+    assert (p - ref.detach()).abs().max().item() < 1e-6  # 1-2 ulp at |p| ~ 4
     assert torch.equal(shadow, p.to(torch.bfloat16))
 
 

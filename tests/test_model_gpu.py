@@ -137,7 +137,9 @@ def test_updater_matches_oracle_update(dev):
     g = torch.Generator().manual_seed(5)
     vp, cvp = torch.randn(T + 1, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g).abs()
     logp = -1.7 + 0.1 * torch.randn(T, N, generator=g)
-    cfg = PPOLagConfig(update_repeats=2, lr=1e-3)
+    # eps = 1e-4 keeps Adam from amplifying round-off-level gradients (e.g. the key-bias gradient, which is
+    # exactly zero in exact arithmetic) into +-lr steps that differ between any two implementations
+    cfg = PPOLagConfig(update_repeats=2, lr=1e-3, eps=1e-4)
     ref_sd, ref_lam, ref_info = oracle_update(sd, ro, vp, cvp, logp, cfg, A, C)
     model = B200SafeActorCritic(A, C, precision="fp32", state_dict=sd, device=dev)
     st = B200RolloutStorage(T, dev)
@@ -147,9 +149,13 @@ def test_updater_matches_oracle_update(dev):
     assert abs(res["lambda"].item() - ref_lam) < 1e-5
     assert abs(res["loss_scalars"][0].item() - ref_info["last_total"]) < 1e-3 * max(1, abs(ref_info["last_total"]))
     mine = model.state_dict()
-    worst = 0.0
+    worst, moved = ("", 0.0), 0.0
     for k, v in ref_sd.items():
         if "text_encoder" in k:
             continue
-        worst = max(worst, (mine[k].cpu() - v).abs().max().item())
-    assert worst < 5e-5, worst  # two Adam steps of lr 1e-3: parameters move by ~2e-3
+        err = (mine[k].cpu() - v).abs().max().item()
+        moved = max(moved, (v - sd[k]).abs().max().item())
+        if err > worst[1]:
+            worst = (k, err)
+    assert moved > 5e-4  # two Adam steps of lr 1e-3 really moved the parameters
+    assert worst[1] < 2e-5, worst
