@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- PPO-Lagrangian update samples/s on synthetic 64-env x 128-step rollouts (BASELINE.json).
+
+A "step" is one whole constrained-PPO update of one rollout: GAE(reward)+GAE(cost) -> update_repeats(4) x
+[3-tower forward, fused PPO-Lagrangian loss fwd+bwd, tower backwards, (N>1: one NCCL all-reduce), fused
+clip+Adam] -> Lagrange-multiplier update.   samples/s = T * N_global * update_repeats / t_step.
+
+  value : rollout already resident in HBM when the timed region starts (every step is treated as a NEW
+          rollout: the observation-derived caches -- token-major features, T5 text encoding -- are rebuilt
+          inside the timed region).
+  e2e   : same metric through the public host API with HOST buffers: pinned-host rollout -> H2D copy into
+          B200RolloutStorage -> PPOLagUpdater.update -> D2H of the loss scalars and lambda, all timed.
+  --impl reference : the CPU restatement of the reference path (oracle/, torch eager fp32 on all host cores)
+          on a bounded sampler-subsample of the same workload.  The reference itself is Python that needs
+          /root/reference, which does not exist on the GPU box; the oracle is pinned against it by
+          tests/golden/ (see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / configs[2]: 64-env x 128-step ObjectNav rollouts, one camera, 32-token prompt
+    "cfg2_64env_128step": dict(T=128, N=64, A=20, C=1, L=32, gflop_per_sample=18.4),
+    # configs[0] (CPU-runnable correctness gate)
+    "cfg1_1env_16step": dict(T=16, N=1, A=6, C=1, L=32, gflop_per_sample=18.4),
+    # configs[3] PickupType head, two cameras (S = 201)
+    "cfg4_32env_256step": dict(T=256, N=32, A=20, C=2, L=32, gflop_per_sample=31.5),
+    "cfg5_128env_128step": dict(T=128, N=128, A=20, C=2, L=32, gflop_per_sample=31.5),
+}
+UPDATE_REPEATS = 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int):
+    """Times the CPU oracle's whole update on a sampler-subsample (sample_N of the N samplers, first sample_T
+    steps, ONE update repeat); returns samples/s and a description."""
+    from oracle.update_oracle import oracle_update  # the one place bench.py executes oracle/
+    from safevla_b200.params import init_state_dict
+    from safevla_b200.synthetic import RolloutSpec, make_rollout
+    from safevla_b200.updater import PPOLagConfig
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = init_state_dict(wl["A"], wl["C"], seed=0)
+    ro = make_rollout(RolloutSpec(sample_T, sample_N, wl["A"], wl["C"], prompt_tokens=wl["L"], seed=1234))
+    g = torch.Generator().manual_seed(0)
+    vp = torch.randn(sample_T + 1, sample_N, 1, generator=g)
+    cvp = torch.randn(sample_T + 1, sample_N, 1, generator=g).abs()
+    logp = -3.0 + 0.05 * torch.randn(sample_T, sample_N, generator=g)
+    cfg = PPOLagConfig(update_repeats=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle_update(sd, ro, vp, cvp, logp, cfg, wl["A"], wl["C"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return sample_T * sample_N / t, t, (f"CPU oracle (torch eager fp32, {torch.get_num_threads()} threads): "
+                                        f"{sample_N} of {wl['N']} samplers x {sample_T} of {wl['T']} steps, 1 of "
+                                        f"{UPDATE_REPEATS} update repeats per step")
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=min(wl["T"], 32), sample_N=1)
+    line = {"impl": "reference", "metric": "ppo_lagrangian_update_samples_per_sec", "value": v, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "T": wl["T"], "N_global": wl["N"], "actions": wl["A"], "cameras": wl["C"],
+                       "prompt_tokens": wl["L"], "update_repeats": UPDATE_REPEATS},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": desc},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def scan_roofline(dev, pk):
+    """GAE + fused loss at a roofline-scale shape (T=128, N=65536): achieved algorithmic GB/s."""
+    from safevla_b200 import _lib as L
+    from safevla_b200 import ops
+    T, N, A = 128, 65536, 20
+    r, c = torch.randn(T, N, device=dev), torch.rand(T, N, device=dev)
+    v, vc = torch.randn(T + 1, N, device=dev), torch.randn(T + 1, N, device=dev)
+    m = (torch.rand(T + 1, N, device=dev) > 0.02).float()
+    out = (torch.empty_like(v), torch.empty_like(vc), torch.empty_like(r), torch.empty_like(c))
+    logits = torch.randn(T * N, A, device=dev)
+    actions = torch.randint(0, A, (T * N,), device=dev)
+    oldlp = torch.full((T * N,), -3.0, device=dev)
+    lam = torch.full((1,), 0.1, device=dev)
+    hp = L.PpoHparams(0.1, 1.0, 0.5, 0.0, 0.0, 1.0 / (T * N), 1.0, 0, 1)
+    dl, dv = torch.empty_like(logits), torch.empty(T * N, device=dev)
+    scal = torch.empty(16, device=dev)
+
+    def t_of(fn, n=10):
+        for _ in range(3):
+            fn()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        for i in range(n):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        return min(ev[i].elapsed_time(ev[i + 1]) for i in range(n)) * 1e-3
+
+    t_gae = t_of(lambda: ops.gae_dual(r, c, v, vc, m, 0.99, 0.95, 1, out=out))
+    lib, ctx = L.load_library(), L.get_ctx()
+
+    def loss():
+        L.check(lib.svla_ppo_lag_fwd_bwd(ctx, logits.data_ptr(), actions.data_ptr(), oldlp.data_ptr(),
+                                         out[2].data_ptr(), out[3].data_ptr(), v.data_ptr(), out[0].data_ptr(), None,
+                                         None, None, None, lam.data_ptr(), hp, scal.data_ptr(), dl.data_ptr(),
+                                         dv.data_ptr(), None, T * N, A, L.stream_ptr()))
+    t_loss = t_of(loss)
+    gae_b, loss_b = 36.0 * T * N, (8.0 * A + 44.0) * T * N
+    return {"shape": f"T={T},N={N},A={A}", "peak_gbs": pk["hbm"], "peak_src": pk["src"],
+            "gae": {"gbs": gae_b / t_gae / 1e9, "frac": gae_b / t_gae / 1e9 / pk["hbm"], "us": t_gae * 1e6},
+            "loss": {"gbs": loss_b / t_loss / 1e9, "frac": loss_b / t_loss / 1e9 / pk["hbm"], "us": t_loss * 1e6}}
+
+
+def run_b200(args, wl, name):
+    import torch.distributed as dist
+
+    from safevla_b200 import _lib as L
+    from safevla_b200 import ops
+    from safevla_b200.model import ACTOR, COST, CRITIC, B200SafeActorCritic
+    from safevla_b200.storage import B200RolloutStorage
+    from safevla_b200.synthetic import RolloutSpec, make_rollout
+    from safevla_b200.updater import PPOLagConfig, PPOLagUpdater
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert wl["N"] % world == 0, "samplers must divide evenly over the ranks"
+    T, A, C = wl["T"], wl["A"], wl["C"]
+    n_local = wl["N"] // world
+    pk = peaks()
+
+    model = B200SafeActorCritic(A, C, precision=args.precision, seed=0, device=dev, chunk_rows=args.chunk_rows,
+                                extras="off", verify_dedupe=False)
+    cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS)
+    upd = PPOLagUpdater(model, cfg)
+    ro = make_rollout(RolloutSpec(T, n_local, A, C, prompt_tokens=wl["L"], seed=1234), rank=rank, pin=True)
+    storage = B200RolloutStorage(T, dev)
+
+    # ---- "collection": value / cost-value predictions and old log-probs from the model's own forward
+    obs_full = {k: v.to(dev) for k, v in ro["observations"].items()}
+    pa_full = torch.cat([torch.zeros(1, n_local, dtype=torch.int64), ro["actions"]], 0).to(dev)
+    mk_full = ro["masks"].to(dev).view(T + 1, n_local)
+    with torch.no_grad():
+        rc = model.prepare(obs_full, T + 1, n_local)
+        outs = {i: model.tower_forward(i, rc, pa_full, mk_full, keep=False, want_logits=(i == ACTOR),
+                                       want_values=(i != ACTOR))[0] for i in (ACTOR, CRITIC, COST)}
+        logp = torch.log_softmax(outs[ACTOR]["logits"][:T], -1).gather(-1, ro["actions"].to(dev).unsqueeze(-1))
+    vp_host = outs[CRITIC]["values"].cpu().pin_memory()
+    cvp_host = outs[COST]["values"].cpu().pin_memory()
+    logp_host = logp.squeeze(-1).cpu().pin_memory()
+    del obs_full, outs, rc
+    model._ctx_cache = None
+    storage.load_rollout(ro, vp_host, cvp_host, logp_host)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        model._ctx_cache = None  # a new rollout every step: rebuild the observation-derived caches
+        return upd.update(storage)
+
+    host_out = torch.empty(18, pin_memory=True)
+
+    def step_e2e():
+        model._ctx_cache = None
+        storage.load_rollout(ro, vp_host, cvp_host, logp_host)  # pinned host -> HBM
+        res = upd.update(storage)
+        host_out[:16].copy_(res["loss_scalars"], non_blocking=True)
+        host_out[16:17].copy_(res["lambda"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+
+    lib = L.load_library()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident metric (+ per-kernel event timing of the dominant GEMM kernel)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    l0 = lib.svla_launch_count()
+    ops.PROFILE = {} if rank == 0 else None
+    t_res = timed(step_resident, args.steps, 0)
+    launches = (lib.svla_launch_count() - l0) // args.steps
+    prof, ops.PROFILE = ops.profile_summary(ops.PROFILE), None
+    # ---- end-to-end metric
+    t_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    samples = T * wl["N"] * UPDATE_REPEATS
+    value, e2e = samples / t_res, samples / t_e2e
+    # roofline of the dominant kernel: summed algorithmic FLOPs / summed event time of its launches
+    roof = None
+    if prof:
+        best = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        kname, rec = best
+        torch.cuda.synchronize()
+        ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
+        peak = pk["tf_sust"]
+        roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "launches_per_step": rec["n"] // args.steps,
+                "share_of_step": rec["ms"] * 1e-3 / (t_res * args.steps), "peak_src": pk["src"] + " (sustained bf16)"}
+    step_tf = value * wl["gflop_per_sample"] / 1e3
+    line = {
+        "metric": "ppo_lagrangian_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": name, "T": T, "N_global": wl["N"], "N_per_rank": n_local, "actions": A, "cameras": C,
+                   "prompt_tokens": wl["L"], "update_repeats": UPDATE_REPEATS, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (1.06 GB of observations per rank-rollout at N=64)",
+                   "precision": args.precision, "chunk_rows": args.chunk_rows},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": storage.h2d_bytes(),
+                "d2h_bytes_per_step": 17 * 4, "ms_per_step": t_e2e * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "step_algorithmic_tflops": {"achieved": step_tf, "peak": pk["tf_sust"], "frac": step_tf / pk["tf_sust"],
+                                    "gflop_per_sample": wl["gflop_per_sample"]},
+    }
+    if world == 1:
+        line["roofline_scan"] = scan_roofline(dev, pk)
+        if not args.no_cpu_baseline:
+            v, t, desc = cpu_sample(wl, 1, 0, sample_T=min(T, 32), sample_N=1)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": desc}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_64env_128step", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk-rows", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        run_b200(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

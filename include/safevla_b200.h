@@ -47,6 +47,8 @@ int svla_ctx_destroy(svla_ctx* ctx);
 const char* svla_last_error(void);
 int svla_version(void);
 int svla_sm_count(svla_ctx* ctx);
+/* number of kernels this library has launched in the calling process (monotonic) */
+unsigned long long svla_launch_count(void);
 
 /* ======================================================================================
  * Scan / elementwise path (HBM bound)
@@ -155,6 +157,8 @@ typedef struct {
 /* C = epi(alpha * op(A) op(B) + bias) [+ residual] -- every nn.Linear / 1x1 Conv2d forward, dgrad
  * and wgrad of the towers (allenact_dino_transformer.py:509-513,532-552; llama/model.py:203-222,355-357,437). */
 int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream stream);
+/* which kernel svla_gemm would run for this descriptor: 1 = fp32-FMA, 2 = tcgen05 */
+int svla_gemm_which(const svla_gemm_desc* d);
 
 /* column sums: out[n] (+)= sum_m x[m,n]  -- bias gradients. */
 int svla_colsum(svla_ctx* ctx, const void* x, int dtype, long long M, int N, long long ldx, float* out,

@@ -61,6 +61,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_last_error": [],
     "svla_version": [],
     "svla_sm_count": [c_p],
+    "svla_launch_count": [],
     "svla_gae_dual": [c_p] + [c_p] * 9 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_p],
     "svla_normalize_advantage": [c_p, c_p, c_p, c_p, c_ll, c_p],
     "svla_ppo_lag_fwd_bwd": [c_p] + [c_p] * 12 + [C.POINTER(PpoHparams)] + [c_p] * 4 + [c_ll, C.c_int, c_p],
@@ -68,6 +69,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_sq_norm": [c_p, c_p, c_ll, c_p, c_p],
     "svla_clip_adam": [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, C.POINTER(AdamHparams), c_p],
     "svla_gemm": [c_p, C.POINTER(GemmDesc), c_p],
+    "svla_gemm_which": [C.POINTER(GemmDesc)],
     "svla_colsum": [c_p, c_p, C.c_int, c_ll, C.c_int, c_ll, c_p, C.c_int, c_p],
     "svla_layernorm_fwd": [c_p, c_p, c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.c_float, c_p, C.c_int, RowMap,
                            c_p, c_p, c_ll, C.c_int, c_p],
@@ -95,7 +97,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_cast_bf16": [c_p, c_p, c_p, c_ll, c_p],
     "svla_hash_rows": [c_p, c_p, c_ll, C.c_int, c_p, c_p],
 }
-_RESTYPES = {"svla_last_error": C.c_char_p}
+_RESTYPES = {"svla_last_error": C.c_char_p, "svla_launch_count": C.c_ulonglong}
 
 _lib: Optional[C.CDLL] = None
 _ctxs: Dict[int, int] = {}

@@ -38,7 +38,13 @@ void svla_set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-#define SVLA_LAUNCH_CHECK() SVLA_CUDA(cudaGetLastError())
+// one call per kernel launch: checks the launch and counts it (svla_launch_count, bench.py's gpu_launches)
+extern unsigned long long g_svla_launches;
+#define SVLA_LAUNCH_CHECK()            \
+  do {                                 \
+    ++g_svla_launches;                 \
+    SVLA_CUDA(cudaGetLastError());     \
+  } while (0)
 
 static inline cudaStream_t as_stream(svla_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 

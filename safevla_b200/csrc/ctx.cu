@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_svla_launches = 0;
 
 void svla_set_error(const char* fmt, ...) {
   va_list ap;
@@ -65,5 +66,6 @@ int svla_ctx_destroy(svla_ctx* ctx) {
 }
 
 int svla_sm_count(svla_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+unsigned long long svla_launch_count(void) { return g_svla_launches; }
 
 }  // extern "C"

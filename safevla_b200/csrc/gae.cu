@@ -212,7 +212,9 @@ extern "C" int svla_normalize_advantage(svla_ctx* ctx, const float* adv, float* 
   int nb = (int)((n + 255) / 256);
   if (nb > 1024) nb = 1024;
   adv_stats_partial<<<nb, 256, 0, as_stream(stream)>>>(adv, n, ctx->partials);
+  SVLA_LAUNCH_CHECK();
   adv_stats_final<<<1, 32, 0, as_stream(stream)>>>(ctx->partials, nb, n, stats);
+  SVLA_LAUNCH_CHECK();
   adv_normalize<<<nb, 256, 0, as_stream(stream)>>>(adv, norm_adv, n, stats);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;

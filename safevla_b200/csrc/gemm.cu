@@ -28,3 +28,9 @@ extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream str
   if (d->impl == 0 && svla_gemm_tc_supported(d)) return svla_gemm_tc(ctx, d, st);
   return svla_gemm_simt(ctx, d, st);
 }
+
+extern "C" int svla_gemm_which(const svla_gemm_desc* d) {
+  if (!d) return 0;
+  if (d->impl == 1) return 1;
+  return svla_gemm_tc_supported(d) ? 2 : 1;
+}

@@ -1,10 +1,528 @@
-// tcgen05 tensor-core GEMM (placeholder until the TMA/TMEM kernel lands in this file).
+// tcgen05 tensor-core GEMM for sm_100a: bf16 operands, fp32 accumulation in TMEM.
+//
+//   C[M,N] = epi(alpha * op(A) op(B) + bias) [+ residual]          (see svla_gemm_desc)
+//
+// One persistent kernel, warp-specialised:
+//   warp 0     TMA producer   cp.async.bulk.tensor (128B swizzle) global -> shared, 4-stage mbarrier ring
+//   warp 1     MMA issuer     one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per
+//                             instruction), accumulators double-buffered in TMEM (2 x BN columns)
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue       tcgen05.ld -> registers -> bias / ReLU / ReLU-mask / residual / accumulate ->
+//                             128-bit global stores; overlaps the next tile's main loop
+// Operand layouts: both K-major (forward: activations x nn.Linear weight), K-major x MN-major (dgrad:
+// dY x W), MN-major x MN-major (wgrad: dY^T x X) -- the UMMA shared-memory descriptors and the TMA boxes
+// differ, the pipeline does not, so no operand is ever transposed in HBM.
+// Split-K (wgrad: K = rows of the batch) writes fp32 slices to the context workspace; a fixed-order
+// reduction kernel applies the epilogue (deterministic).
+#include <cuda.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 
-void svla_tmap_cache_free(void* cache) { (void)cache; }
-bool svla_gemm_tc_supported(const svla_gemm_desc* d) { (void)d; return false; }
+namespace {
+
+constexpr int BM = 128, BK = 64, kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// UMMA shared-memory descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+struct TcArgs {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split;  // kb = K blocks of BK
+  void* C; long long ldc; int dtypeC;
+  const float* bias;
+  const void* residual; long long ldr; int dtypeR;
+  const void* aux; long long ldaux; int dtypeAux;
+  int epilogue, accumulate;
+  float alpha;
+  float* ws;
+};
+
+__device__ __forceinline__ float ld_elem(const void* p, int dt, long long i) {
+  return dt == SVLA_F32 ? __ldg(reinterpret_cast<const float*>(p) + i)
+                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+// loads 8 consecutive elements (16-byte aligned for bf16, 32-byte for f32)
+__device__ __forceinline__ void ld8(const void* p, int dt, long long i, float* o) {
+  if (dt == SVLA_F32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i + 4));
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      o[2 * j] = f.x; o[2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void st8(void* p, int dt, long long i, const float* v) {
+  if (dt == SVLA_F32) {
+    float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = u;
+  }
+}
+
+// AMN / BMN: operand is MN-major (its M / N dimension is the contiguous one in global memory)
+template <int BN, bool AMN, bool BMN>
+__global__ void __launch_bounds__(kThreads, 1)
+svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+  constexpr int kStages = (BN == 256) ? 4 : 6;
+  constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = 2 * BN;  // double-buffered accumulator
+  // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_work = g.tiles_m * g.tiles_n * g.splits;
+  const int kb_total = (g.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tn = w % g.tiles_n, tm = (w / g.tiles_n) % g.tiles_m, sp = w / (g.tiles_n * g.tiles_m);
+        const int kb0 = sp * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          if (!AMN) {
+            tma_load_2d(sa, &mapA, &full_bar[stage], kb * BK, tm * BM);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)  // boxes {64 m, 64 k}
+              tma_load_2d(sa + j * (BK * 128), &mapA, &full_bar[stage], tm * BM + j * 64, kb * BK);
+          }
+          if (!BMN) {
+            tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, tn * BN);  // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &mapB, &full_bar[stage], tn * BN + j * 64, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int sp = w / (g.tiles_n * g.tiles_m);
+      const int kb0 = sp * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 8-row groups 1024 B apart, +32 B per 16-element k step inside the 128 B swizzle row.
+            // MN-major: 64-element chunks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO),
+            //           +16 rows * 128 B per k step.
+            const uint64_t da = AMN ? umma_desc(sa + k * 2048, BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = BMN ? umma_desc(sb + k * 2048, BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue ================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tn = w % g.tiles_n, tm = (w / g.tiles_n) % g.tiles_m, sp = w / (g.tiles_n * g.tiles_m);
+      const int m = tm * BM + q * 32 + lane;
+      const bool row_ok = m < g.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = tn * BN + c * 32;
+        if (n0 >= g.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_wait_ld();
+        if (row_ok) {
+          if (g.splits > 1) {
+            float* dst = g.ws + ((size_t)sp * g.M + m) * g.N + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) * g.alpha;
+              if (g.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (g.epilogue == SVLA_EPI_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+              } else if (g.epilogue == SVLA_EPI_RELU_MASK) {
+                float a[8];
+                ld8(g.aux, g.dtypeAux, (long long)m * g.ldaux + n0 + j, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
+              }
+              if (g.residual) {
+                float a[8];
+                ld8(g.residual, g.dtypeR, (long long)m * g.ldr + n0 + j, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += a[e];
+              }
+              const long long ci = (long long)m * g.ldc + n0 + j;
+              if (g.accumulate) {
+                float a[8];
+                ld8(g.C, g.dtypeC, ci, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += a[e];
+              }
+              st8(g.C, g.dtypeC, ci, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// fixed-order split-K fold + epilogue
+__global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(TcArgs g) {
+  const long long total = (long long)g.M * g.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / g.N), n = (int)(i % g.N);
+    float v = 0.f;
+    for (int s = 0; s < g.splits; ++s) v += g.ws[(size_t)s * total + i];
+    v *= g.alpha;
+    if (g.bias) v += __ldg(g.bias + n);
+    if (g.epilogue == SVLA_EPI_RELU) v = fmaxf(v, 0.f);
+    else if (g.epilogue == SVLA_EPI_RELU_MASK) v = ld_elem(g.aux, g.dtypeAux, (long long)m * g.ldaux + n) > 0.f ? v : 0.f;
+    if (g.residual) v += ld_elem(g.residual, g.dtypeR, (long long)m * g.ldr + n);
+    const long long ci = (long long)m * g.ldc + n;
+    if (g.accumulate) v += ld_elem(g.C, g.dtypeC, ci);
+    if (g.dtypeC == SVLA_F32) reinterpret_cast<float*>(g.C)[ci] = v;
+    else reinterpret_cast<__nv_bfloat16*>(g.C)[ci] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapCache {
+  std::mutex mu;
+  std::map<std::tuple<const void*, long long, long long, long long, int, int>, CUtensorMap> maps;
+};
+
+// 2-D bf16 tensor map: inner (contiguous) extent, outer extent, outer stride ld (elements), box {bi, bo}
+int make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
+              CUtensorMap* out) {
+  if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
+  TmapCache* tc = reinterpret_cast<TmapCache*>(ctx->tmap_cache);
+  const auto key = std::make_tuple(ptr, inner, outer, ld, bi, bo);
+  {
+    std::lock_guard<std::mutex> lk(tc->mu);
+    auto it = tc->maps.find(key);
+    if (it != tc->maps.end()) {
+      *out = it->second;
+      return SVLA_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    svla_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SVLA_ERR_INTERNAL;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bi, (cuuint32_t)bo};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    svla_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r, ptr,
+                   inner, outer, ld, bi, bo);
+    return SVLA_ERR_INTERNAL;
+  }
+  std::lock_guard<std::mutex> lk(tc->mu);
+  if (tc->maps.size() > 8192) tc->maps.clear();
+  tc->maps[key] = *out;
+  return SVLA_OK;
+}
+
+template <int BN, bool AMN, bool BMN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
+  constexpr int kStages = (BN == 256) ? 4 : 6;
+  constexpr size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  auto kern = svla_gemm_tc_kernel<BN, AMN, BMN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, smem, st>>>(ma, mb, g);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+void svla_tmap_cache_free(void* cache) { delete reinterpret_cast<TmapCache*>(cache); }
+
+bool svla_gemm_tc_supported(const svla_gemm_desc* d) {
+  if (d->dtypeA != SVLA_BF16 || d->dtypeB != SVLA_BF16) return false;
+  if (d->transA && !d->transB) {
+    // MN x MN (wgrad)
+  } else if (!d->transA) {
+    // K x K (transB) or K x MN (!transB)
+  } else {
+    return false;  // MN-major A with K-major B is not needed by the towers
+  }
+  if (d->M < 64 || d->N < 32 || d->N % 32 != 0 || d->K < 64) return false;
+  if (d->lda % 8 || d->ldb % 8 || !al16(d->A) || !al16(d->B)) return false;
+  const int esC = d->dtypeC == SVLA_F32 ? 4 : 2;
+  if (!al16(d->C) || (d->ldc * esC) % 16) return false;
+  if (d->bias && !al16(d->bias)) return false;
+  if (d->residual && (!al16(d->residual) || (d->ldr * (d->dtypeR == SVLA_F32 ? 4 : 2)) % 16)) return false;
+  if (d->aux && (!al16(d->aux) || (d->ldaux * (d->dtypeAux == SVLA_F32 ? 4 : 2)) % 16)) return false;
+  return true;
+}
+
 int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
-  (void)ctx; (void)d; (void)st;
-  svla_set_error("tcgen05 GEMM not built");
-  return SVLA_ERR_INTERNAL;
+  const bool amn = d->transA != 0, bmn = d->transB == 0;
+  const int BN = (d->N >= 256) ? 256 : 128;
+  TcArgs g;
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.tiles_m = (d->M + BM - 1) / BM;
+  g.tiles_n = (d->N + BN - 1) / BN;
+  const int kb_total = (d->K + BK - 1) / BK;
+  int splits = 1;
+  const int tiles = g.tiles_m * g.tiles_n;
+  if (tiles * 2 <= ctx->sm_count && kb_total >= 32) {
+    splits = std::min({ctx->sm_count / tiles, kb_total / 8, 32});
+    const size_t per = (size_t)d->M * d->N * sizeof(float);
+    splits = (int)std::min<size_t>((size_t)splits, ctx->ws_bytes / std::max<size_t>(per, 1));
+    splits = std::max(splits, 1);
+  }
+  g.kb_per_split = (kb_total + splits - 1) / splits;
+  g.splits = (kb_total + g.kb_per_split - 1) / g.kb_per_split;
+  g.C = d->C; g.ldc = d->ldc; g.dtypeC = d->dtypeC;
+  g.bias = d->bias;
+  g.residual = d->residual; g.ldr = d->ldr; g.dtypeR = d->dtypeR;
+  g.aux = d->aux; g.ldaux = d->ldaux; g.dtypeAux = d->dtypeAux;
+  g.epilogue = d->epilogue; g.accumulate = d->accumulate; g.alpha = d->alpha;
+  g.ws = reinterpret_cast<float*>(ctx->ws);
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!amn) rc = make_tmap(ctx, d->A, d->K, d->M, d->lda, BK, BM, &ma);       // [M rows][K]  box {64, 128}
+  else rc = make_tmap(ctx, d->A, d->M, d->K, d->lda, 64, BK, &ma);            // [K rows][M]  box {64, 64}
+  if (rc) return rc;
+  if (!bmn) rc = make_tmap(ctx, d->B, d->K, d->N, d->ldb, BK, BN, &mb);       // [N rows][K]  box {64, BN}
+  else rc = make_tmap(ctx, d->B, d->N, d->K, d->ldb, 64, BK, &mb);            // [K rows][N]  box {64, 64}
+  if (rc) return rc;
+
+  const int grid = std::min(tiles * g.splits, ctx->sm_count);
+  if (BN == 256) {
+    if (!amn && !bmn) rc = launch_tc<256, false, false>(ma, mb, g, grid, st);
+    else if (!amn && bmn) rc = launch_tc<256, false, true>(ma, mb, g, grid, st);
+    else rc = launch_tc<256, true, true>(ma, mb, g, grid, st);
+  } else {
+    if (!amn && !bmn) rc = launch_tc<128, false, false>(ma, mb, g, grid, st);
+    else if (!amn && bmn) rc = launch_tc<128, false, true>(ma, mb, g, grid, st);
+    else rc = launch_tc<128, true, true>(ma, mb, g, grid, st);
+  }
+  if (rc) return rc;
+  if (g.splits > 1) {
+    const long long total = (long long)d->M * d->N;
+    const int rb = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
+    tc_splitk_reduce_kernel<<<rb, 256, 0, st>>>(g);
+    SVLA_LAUNCH_CHECK();
+  }
+  return SVLA_OK;
 }

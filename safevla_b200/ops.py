@@ -147,7 +147,27 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     if aux is not None:
         d.aux, d.ldaux, d.dtypeAux = ptr(aux), aux.stride(0), dt(aux)
     d.epilogue, d.accumulate, d.alpha, d.impl = epilogue, int(accumulate), alpha, impl
+    if PROFILE is None:
+        check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
+        return out
+    # bench.py: CUDA-event timing of every GEMM launch on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    which = "svla_gemm_tc_kernel" if _lib().svla_gemm_which(C.byref(d)) == 2 else "gemm_simt_kernel"
+    e0.record()
     check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
+    e1.record()
+    PROFILE.setdefault(which, []).append((2.0 * M * N * K, e0, e1))
+    return out
+
+
+PROFILE = None  # set to {} by bench.py to collect per-launch GEMM timings
+
+
+def profile_summary(prof):
+    """{kernel: {flops, ms, n}} from the recorded events (call after a device synchronize)."""
+    out = {}
+    for k, recs in (prof or {}).items():
+        out[k] = {"flops": sum(r[0] for r in recs), "ms": sum(r[1].elapsed_time(r[2]) for r in recs), "n": len(recs)}
     return out
 
 

@@ -409,3 +409,51 @@ def test_nchw_tokens_copy_fill_hash(dev):
     assert h[10] == h[3] and torch.unique(h).numel() == 63
     rows[10, 999] ^= 1
     assert _ops().hash_rows(rows)[10] != h[3]
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 512), (1872, 1536, 512), (1000, 384, 2048),
+                                   (117 * 64, 2048, 512), (70, 128, 64), (512, 512, 117 * 256)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False)])
+def test_gemm_tcgen05(dev, M, N, K, ta, tb):
+    if ta and M % 8:
+        pytest.skip("MN-major A needs a 16-byte aligned leading dimension (falls back to the FMA kernel)")
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = (torch.randn((K, M) if ta else (M, K), generator=g) * 0.5).to(dev, torch.bfloat16)
+    B = (torch.randn((N, K) if tb else (K, N), generator=g) * 0.5).to(dev, torch.bfloat16)
+    a = (A.t() if ta else A).double()
+    b = (B.t() if tb else B).double()
+    ref = a @ b
+    scale = ref.abs().max().item()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    _ops().gemm(A, B, out, trans_a=ta, trans_b=tb, impl=2)
+    assert (out.double() - ref).abs().max().item() < 1e-2 * scale
+    # epilogues: bias + relu + residual, bf16 out
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+    _ops().gemm(A, B, out, trans_a=ta, trans_b=tb, bias=bias, residual=res, epilogue=_L().EPI_RELU, impl=2)
+    exp = torch.relu(ref + bias.double()) + res.double()
+    assert (out.double() - exp).abs().max().item() < 1e-2 * scale
+    # relu-mask + accumulate into fp32 (exact fp32 accumulation of bf16 products up to summation order)
+    aux = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+    acc = torch.randn(M, N, generator=g).to(dev)
+    acc0 = acc.clone()
+    _ops().gemm(A, B, acc, trans_a=ta, trans_b=tb, aux=aux, epilogue=_L().EPI_RELU_MASK, accumulate=True, impl=2)
+    exp2 = acc0.double() + ref * (aux.double() > 0)
+    assert (acc.double() - exp2).abs().max().item() < 2e-5 * max(scale, 1.0) * max(1.0, (K / 512) ** 0.5)
+
+
+def test_gemm_tcgen05_strided_and_repeat(dev):
+    # CLS-row view (lda = S*D), column-sliced weight, repeated launches reuse cached tensor maps
+    S, D, R = 117, 512, 300
+    x = (torch.randn(R, S * D, device=dev) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(3 * D, D, device=dev) * 0.1).to(torch.bfloat16)
+    out = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        _ops().gemm(x[:, :D], w[0:D], out, trans_b=True, impl=2)
+    ref = x[:, :D].double() @ w[0:D].double().t()
+    assert (out.double() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    qkv = torch.empty(R, 3 * D, device=dev, dtype=torch.bfloat16)
+    _ops().gemm(x[:, :D], w, qkv, trans_b=True, impl=2)
+    ref = x[:, :D].double() @ w.double().t()
+    assert (qkv.double() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
