@@ -203,6 +203,9 @@ int svla_attn_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const v
                   const float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,
                   svla_stream stream);
 
+/* test hook: 0 = auto (tcgen05 kernel for bf16, S <= 128; CUDA-core kernel otherwise), 1 = CUDA-core, 2 = tcgen05 */
+int svla_set_attn_impl(int impl);
+
 /* Single-query attention of the LAST fusion layer: only output token 0 of the fusion transformer is
  * consumed (allenact_dino_transformer.py:708), so its query/out-proj/FFN run for that row alone.
  * q [B, H*dh] (ldq), k/v rows b*S+s (ldkv), o [B, H*dh]; lse [B,H]. */

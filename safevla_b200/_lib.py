@@ -81,6 +81,7 @@ PROTOTYPES: Dict[str, list] = {
                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
     "svla_attn_bwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_p, c_ll, C.c_int, c_p, c_p,
                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
+    "svla_set_attn_impl": [C.c_int],
     "svla_attn_cls_fwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, C.c_int, c_p, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_float, c_p],
     "svla_attn_cls_bwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, C.c_int, c_p,

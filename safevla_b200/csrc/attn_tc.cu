@@ -1,0 +1,492 @@
+// tcgen05 attention for the towers' short sequences (S <= 128 tokens, head dim 64, bf16):
+//   fusion block (S = 117, no mask) and decoder (T <= 128, trajectory-causal mask from traj_index).
+// One (sequence, head) per work item, persistent CTAs of 128 threads; thread i owns query row i.
+//
+// forward:   TMA(Q,K,V) -> S = Q K^T (tcgen05, fp32 in TMEM) -> row softmax from TMEM (exp2, fp32) -> P (bf16,
+//            128B-swizzled in shared memory) -> O = P V (tcgen05) -> O / rowsum -> global; saves log-sum-exp.
+// backward:  TMA(Q,K,V,dO) -> S = Q K^T, dP = dO V^T -> P = exp(S - lse), dS = P (dP - delta) ->
+//            dV = P^T dO, dK = dS^T Q, dQ = dS K (three tcgen05 GEMMs out of the same shared-memory tiles: P/dS are
+//            written once in a layout that is K-major for dQ and MN-major for dV/dK; Q, K, V, dO are consumed
+//            exactly as TMA lands them).
+// Rows/columns >= S of the 128-wide tile come from the neighbouring sequence (or TMA zero fill): masked to exact
+// zeros before they can reach an accumulator.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+int svla_make_tmap_bf16(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
+                        CUtensorMap* out);  // gemm_tc.cu
+
+namespace {
+
+constexpr int DH = 64, TS = 128;  // tile: 128 queries x 128 keys
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// [128 rows x 64] bf16 operand tile as TMA lands it (row = 128 B, 128B swizzle):
+//   K-major view  (rows = M/N, 64 = K): k-step kk (16 elements) -> +32 B
+//   MN-major view (rows = K, 64 = M/N): k-step kk (16 rows)     -> +2048 B
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int kk) { return umma_desc(base + kk * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mnmajor64(uint32_t base, int kk) { return umma_desc(base + kk * 2048, 8192, 1024); }
+// [128 rows x 128] bf16 P / dS tile written by the threads as two 64-column chunks of [128 rows x 128 B]:
+//   K-major view  (rows = M queries, 128 = K keys): k-step kk -> chunk kk/4, +32 B * (kk%4)
+//   MN-major view (rows = K queries, 128 = M keys, two 64-chunks 16384 B apart): k-step kk -> +2048 B
+__device__ __forceinline__ uint64_t desc_p_kmajor(uint32_t base, int kk) {
+  return umma_desc(base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_p_mnmajor(uint32_t base, int kk) { return umma_desc(base + kk * 2048, 16384, 1024); }
+
+// write 8 consecutive bf16 (columns c8*8 .. +8 of row i) of a P / dS tile
+__device__ __forceinline__ void store_p8(uint8_t* base, int i, int c8, const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  const int chunk = c8 >> 3, cc = c8 & 7;
+  *reinterpret_cast<uint4*>(base + chunk * 16384 + i * 128 + ((cc ^ (i & 7)) << 4)) = u;
+}
+
+struct AttnTcArgs {
+  int mode, B, S, H;
+  float scale;
+  const int64_t* traj;
+  float* lse;
+  __nv_bfloat16* o; long long ldo;
+  const __nv_bfloat16* o_in; const __nv_bfloat16* d_o;
+  __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long ldd;
+};
+
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t* r = half ? r1 : r0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h[e] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]) * mul, __uint_as_float(r[j + 2 * e + 1]) * mul);
+      *reinterpret_cast<uint4*>(dst + half * 32 + j) = u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                   const __grid_constant__ CUtensorMap mv, AttnTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;             // 16 KB each
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sP = smem + 49152;     // 32 KB
+  int* sTraj = reinterpret_cast<int*>(smem + 81920);                       // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + 512);        // load, mma
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t kCols = 256;  // S: [0,128), O: [128,192)
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int S = a.S;
+  const float sl2 = a.scale * kLog2e;
+  uint32_t ph_load = 0, ph_mma = 0;
+  for (int w = blockIdx.x; w < a.B * a.H; w += gridDim.x) {
+    const int b = w / a.H, h = w % a.H;
+    const int row0 = b * S;
+    if (tid == 0) {
+      mbar_expect_tx(&bars[0], 3 * 16384);
+      tma_load_2d(sQ, &mq, &bars[0], h * DH, row0);
+      tma_load_2d(sK, &mk, &bars[0], h * DH, row0);
+      tma_load_2d(sV, &mv, &bars[0], h * DH, row0);
+    }
+    if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) sTraj[tid] = (tid < S) ? (int)a.traj[row0 + tid] : -1 - tid;
+    mbar_wait(&bars[0], ph_load);
+    ph_load ^= 1;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t q = smem_u32(sQ), k = smem_u32(sK);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk)
+        umma_bf16(tmem, desc_kmajor(q, kk), desc_kmajor(k, kk), idesc(128, 128, false, false), kk > 0);
+      umma_commit(&bars[1]);
+    }
+    __syncthreads();  // sTraj visible
+    mbar_wait(&bars[1], ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+    // ---- softmax of row i = tid
+    const int i = tid;
+    const int my_traj = (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ? sTraj[i] : 0;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      if (c * 32 >= S) break;
+      uint32_t r[32];
+      tmem_ld32(tmem + lane_base + c * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        bool ok = col < S;
+        if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
+        if (ok) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+    }
+    const float mxs = (mx == -INFINITY) ? 0.f : mx * sl2;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      if (c * 32 < S) {
+        tmem_ld32(tmem + lane_base + c * 32, r);
+        tmem_wait_ld();
+      }
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = c * 32 + j8 * 8 + e;
+          bool ok = col < S && i < S;
+          if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
+          p[e] = ok ? exp2f(__uint_as_float(r[j8 * 8 + e]) * sl2 - mxs) : 0.f;
+          sum += p[e];
+        }
+        store_p8(sP, i, c * 4 + j8, p);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t p = smem_u32(sP), v = smem_u32(sV);
+#pragma unroll
+      for (int kk = 0; kk < TS / 16; ++kk)
+        umma_bf16(tmem + 128, desc_p_kmajor(p, kk), desc_mnmajor64(v, kk), idesc(128, 64, false, true), kk > 0);
+      umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+    {
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tmem + lane_base + 128, r0);
+      tmem_ld32(tmem + lane_base + 160, r1);
+      tmem_wait_ld();
+      if (i < S) {
+        store_row64(a.o + (long long)(row0 + i) * a.ldo + h * DH, r0, r1, 1.f / sum);
+        if (a.lse) a.lse[((long long)b * a.H + h) * S + i] = mx * a.scale + __logf(sum);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // all TMEM reads / smem reads of this item are done before the next item reuses them
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(128)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                   const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo, AttnTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sdO = smem + 49152;
+  uint8_t* sP = smem + 65536;    // 32 KB
+  uint8_t* sdS = smem + 98304;   // 32 KB
+  int* sTraj = reinterpret_cast<int*>(smem + 131072);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072 + 512);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t kCols = 512;  // S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int S = a.S;
+  const float sl2 = a.scale * kLog2e;
+  uint32_t ph_load = 0, ph_mma = 0;
+  for (int w = blockIdx.x; w < a.B * a.H; w += gridDim.x) {
+    const int b = w / a.H, h = w % a.H;
+    const int row0 = b * S;
+    const int i = tid;
+    if (tid == 0) {
+      mbar_expect_tx(&bars[0], 4 * 16384);
+      tma_load_2d(sQ, &mq, &bars[0], h * DH, row0);
+      tma_load_2d(sK, &mk, &bars[0], h * DH, row0);
+      tma_load_2d(sV, &mv, &bars[0], h * DH, row0);
+      tma_load_2d(sdO, &mdo, &bars[0], h * DH, row0);
+    }
+    if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) sTraj[tid] = (tid < S) ? (int)a.traj[row0 + tid] : -1 - tid;
+    // delta_i = dO_i . O_i and lse_i straight from global memory (overlaps the TMA)
+    float delta = 0.f, lse2 = 0.f;
+    if (i < S) {
+      const uint4* po = reinterpret_cast<const uint4*>(a.o_in + (long long)(row0 + i) * a.ldo + h * DH);
+      const uint4* pd = reinterpret_cast<const uint4*>(a.d_o + (long long)(row0 + i) * a.ldo + h * DH);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 uo = __ldg(po + j), ud = __ldg(pd + j);
+        const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&uo);
+        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fo = __bfloat1622float2(ho[e]), fd = __bfloat1622float2(hd[e]);
+          delta = fmaf(fo.x, fd.x, delta);
+          delta = fmaf(fo.y, fd.y, delta);
+        }
+      }
+      lse2 = a.lse[((long long)b * a.H + h) * S + i] * kLog2e;
+    }
+    mbar_wait(&bars[0], ph_load);
+    ph_load ^= 1;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t q = smem_u32(sQ), k = smem_u32(sK), v = smem_u32(sV), d = smem_u32(sdO);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk)
+        umma_bf16(tmem, desc_kmajor(q, kk), desc_kmajor(k, kk), idesc(128, 128, false, false), kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk)
+        umma_bf16(tmem + 128, desc_kmajor(d, kk), desc_kmajor(v, kk), idesc(128, 128, false, false), kk > 0);
+      umma_commit(&bars[1]);
+    }
+    __syncthreads();
+    mbar_wait(&bars[1], ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+    const int my_traj = (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ? sTraj[i] : 0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rs[32], rp[32];
+      if (c * 32 < S) {
+        tmem_ld32(tmem + lane_base + c * 32, rs);
+        tmem_ld32(tmem + lane_base + 128 + c * 32, rp);
+        tmem_wait_ld();
+      }
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        float p[8], ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = c * 32 + j8 * 8 + e;
+          bool ok = col < S && i < S;
+          if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
+          p[e] = ok ? exp2f(__uint_as_float(rs[j8 * 8 + e]) * sl2 - lse2) : 0.f;
+          ds[e] = ok ? p[e] * (__uint_as_float(rp[j8 * 8 + e]) - delta) : 0.f;
+        }
+        store_p8(sP, i, c * 4 + j8, p);
+        store_p8(sdS, i, c * 4 + j8, ds);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t q = smem_u32(sQ), k = smem_u32(sK), d = smem_u32(sdO), p = smem_u32(sP), s = smem_u32(sdS);
+#pragma unroll
+      for (int kk = 0; kk < TS / 16; ++kk)  // dV[keys, dh] = P^T dO
+        umma_bf16(tmem + 256, desc_p_mnmajor(p, kk), desc_mnmajor64(d, kk), idesc(128, 64, true, true), kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < TS / 16; ++kk)  // dK[keys, dh] = dS^T Q
+        umma_bf16(tmem + 320, desc_p_mnmajor(s, kk), desc_mnmajor64(q, kk), idesc(128, 64, true, true), kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < TS / 16; ++kk)  // dQ[queries, dh] = dS K
+        umma_bf16(tmem + 384, desc_p_kmajor(s, kk), desc_mnmajor64(k, kk), idesc(128, 64, false, true), kk > 0);
+      umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+    {
+      uint32_t r0[32], r1[32];
+      const long long orow = (long long)(row0 + i) * a.ldd + h * DH;
+      tmem_ld32(tmem + lane_base + 256, r0);
+      tmem_ld32(tmem + lane_base + 288, r1);
+      tmem_wait_ld();
+      if (i < S) store_row64(a.dv + orow, r0, r1, 1.f);
+      tmem_ld32(tmem + lane_base + 320, r0);
+      tmem_ld32(tmem + lane_base + 352, r1);
+      tmem_wait_ld();
+      if (i < S) store_row64(a.dk + orow, r0, r1, a.scale);
+      tmem_ld32(tmem + lane_base + 384, r0);
+      tmem_ld32(tmem + lane_base + 416, r1);
+      tmem_wait_ld();
+      if (i < S) store_row64(a.dq + orow, r0, r1, a.scale);
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kCols) : "memory");
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool svla_attn_tc_supported(int mode, int dtype, int S, int dh, long long ld, long long ldo, const void* q,
+                            const void* k, const void* v, const void* o) {
+  return dtype == SVLA_BF16 && dh == DH && S >= 1 && S <= TS && (mode == SVLA_ATTN_FULL || mode == SVLA_ATTN_TRAJ_CAUSAL) &&
+         ld % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) && al16(v) && al16(o);
+}
+
+int svla_attn_tc_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                     long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  const long long rows = (long long)B * S;
+  int rc;
+  if ((rc = svla_make_tmap_bf16(ctx, q, (long long)H * DH, rows, ld, DH, TS, &mq))) return rc;
+  if ((rc = svla_make_tmap_bf16(ctx, k, (long long)H * DH, rows, ld, DH, TS, &mk))) return rc;
+  if ((rc = svla_make_tmap_bf16(ctx, v, (long long)H * DH, rows, ld, DH, TS, &mv))) return rc;
+  AttnTcArgs a{};
+  a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = lse;
+  a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo;
+  constexpr size_t smem = 81920 + 512 + 64 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int grid = std::min(B * H, 2 * ctx->sm_count);
+  attn_tc_fwd_kernel<<<grid, 128, smem, st>>>(mq, mk, mv, a);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+int svla_attn_tc_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
+                     const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
+                     const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st) {
+  CUtensorMap mq, mk, mv, mdo;
+  const long long rows = (long long)B * S;
+  int rc;
+  if ((rc = svla_make_tmap_bf16(ctx, q, (long long)H * DH, rows, ld, DH, TS, &mq))) return rc;
+  if ((rc = svla_make_tmap_bf16(ctx, k, (long long)H * DH, rows, ld, DH, TS, &mk))) return rc;
+  if ((rc = svla_make_tmap_bf16(ctx, v, (long long)H * DH, rows, ld, DH, TS, &mv))) return rc;
+  if ((rc = svla_make_tmap_bf16(ctx, d_o, (long long)H * DH, rows, ldo, DH, TS, &mdo))) return rc;
+  AttnTcArgs a{};
+  a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = const_cast<float*>(lse);
+  a.o_in = reinterpret_cast<const __nv_bfloat16*>(o); a.d_o = reinterpret_cast<const __nv_bfloat16*>(d_o); a.ldo = ldo;
+  a.dq = reinterpret_cast<__nv_bfloat16*>(dq); a.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.ldd = ldd;
+  constexpr size_t smem = 131072 + 512 + 64 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int grid = std::min(B * H, ctx->sm_count);
+  attn_tc_bwd_kernel<<<grid, 128, smem, st>>>(mq, mk, mv, mdo, a);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}

@@ -188,14 +188,35 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(const float* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long M, int N, long long ldx,
                                                              long long chunk, float* __restrict__ partial) {
+  // 64 column groups (4 columns each) x 4 row lanes; every thread keeps 4 independent row loads in flight
+  __shared__ float4 red[4][64];
   const long long r0 = blockIdx.x * chunk, r1 = min(M, r0 + chunk);
-  for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+  const int cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  for (int c0 = 0; c0 < N; c0 += 256) {
+    const int c = c0 + cg * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long r = r0; r < r1; ++r) {
-      const float4 v = load4<T>(x + r * ldx + c);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (c < N) {
+      long long r = r0 + rl;
+      for (; r + 12 < r1; r += 16) {
+        const float4 v0 = load4<T>(x + r * ldx + c), v1 = load4<T>(x + (r + 4) * ldx + c);
+        const float4 v2 = load4<T>(x + (r + 8) * ldx + c), v3 = load4<T>(x + (r + 12) * ldx + c);
+        s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y);
+        s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; r < r1; r += 4) {
+        const float4 v = load4<T>(x + r * ldx + c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
-    *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * N + c) = s;
+    __syncthreads();
+    red[rl][cg] = s;
+    __syncthreads();
+    if (rl == 0 && c < N) {
+      const float4 a = red[0][cg], b = red[1][cg], d = red[2][cg], e = red[3][cg];
+      *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * N + c) =
+          make_float4((a.x + b.x) + (d.x + e.x), (a.y + b.y) + (d.y + e.y), (a.z + b.z) + (d.z + e.z),
+                      (a.w + b.w) + (d.w + e.w));
+    }
   }
 }
 template <typename T>

@@ -6,9 +6,9 @@
 //
 // Algorithmic traffic: 20 B read + 16 B written per (t, n) for the stream pair (36 B).
 // Two kernels:
-//   * march: one thread per sampler n walking t = T-1..0, coalesced across n, loads issued
-//     kU steps ahead of the dependent chain.  Same operation order and roundings as the
-//     sequential recursion (explicit _rn intrinsics, no FMA contraction) -> bit-exact.
+//   * march: lanes = samplers (coalesced), warps = 16-step time chunks held in registers; chunks run their
+//     dependent chains latest-first, handing g over through shared memory.  Same operation order and
+//     roundings as the sequential recursion (explicit _rn intrinsics, no FMA contraction) -> bit-exact.
 //   * warp scan: one warp per sampler, each lane owns a block of consecutive steps; the
 //     recursion is the affine map g -> delta + a*g, composed with a warp suffix scan.
 //     For small N (BASELINE shapes: 64 samplers), where the march has no parallelism.
@@ -16,7 +16,6 @@
 
 namespace {
 
-constexpr int kU = 8;
 
 struct GaeArgs {
   const float* r[2];
@@ -28,17 +27,32 @@ struct GaeArgs {
   float gamma, gl;
 };
 
-__global__ void __launch_bounds__(128) gae_march_kernel(GaeArgs a) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= a.N) return;
+// Block = 32 samplers (lanes, coalesced) x kW time-chunks (warps) of kL steps.  Every thread first pulls its
+// whole chunk into registers (all loads of the block in flight at once: 32 x kW x kL x 20 B), then the chunks run
+// their short dependent chains one after the other, latest first, handing g across through shared memory --
+// the exact operation order of the sequential recursion, so the result is bit-identical to it, while HBM sees
+// one fully parallel pass (20 B read + 16 B written per (t, n)).
+constexpr int kL = 16, kW = 8;
+
+__global__ void __launch_bounds__(32 * kW) gae_march_kernel(GaeArgs a) {
+  __shared__ float sG[2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const bool live = n < a.N;
   const int T = a.T, N = a.N;
-  float g[2] = {0.f, 0.f};
-  for (int s = 0; s < a.ns; ++s) a.ret[s][(size_t)T * N + n] = a.v[s][(size_t)T * N + n];
-  for (int t1 = T; t1 > 0; t1 -= kU) {
-    const int t0 = max(t1 - kU, 0), cnt = t1 - t0;
-    float rr[2][kU], vv[2][kU + 1], mm[kU];
+  if (warp == 0) {
+    sG[0][lane] = 0.f;
+    sG[1][lane] = 0.f;
+    if (live)
+      for (int s = 0; s < a.ns; ++s) a.ret[s][(size_t)T * N + n] = a.v[s][(size_t)T * N + n];
+  }
+  const int span = kL * kW;
+  for (int sup = (T + span - 1) / span - 1; sup >= 0; --sup) {
+    const int t0 = sup * span + warp * kL;
+    const int cnt = live ? max(0, min(kL, T - t0)) : 0;
+    float rr[2][kL], vv[2][kL + 1], mm[kL];
 #pragma unroll
-    for (int j = 0; j < kU; ++j) {
+    for (int j = 0; j < kL; ++j) {
       if (j < cnt) {
         const size_t off = (size_t)(t0 + j) * N + n;
         mm[j] = __ldg(a.m + off + N);  // m_{t+1}
@@ -51,31 +65,38 @@ __global__ void __launch_bounds__(128) gae_march_kernel(GaeArgs a) {
       }
     }
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (s < a.ns) vv[s][kU] = 0.f;
-#pragma unroll
-    for (int j = 0; j < kU; ++j)  // V_{t+1} of the last step of the chunk
+    for (int j = 0; j < kL; ++j)  // V_{t+1} of the chunk's last step
       if (j == cnt - 1) {
 #pragma unroll
         for (int s = 0; s < 2; ++s)
           if (s < a.ns) vv[s][j + 1] = __ldg(a.v[s] + (size_t)(t0 + j + 1) * N + n);
       }
+    __syncthreads();  // sG initialised / handed over from the previous super-chunk
+#pragma unroll 1
+    for (int c = kW - 1; c >= 0; --c) {
+      if (warp == c && cnt > 0) {
+        float g[2] = {sG[0][lane], sG[1][lane]};
 #pragma unroll
-    for (int j = kU - 1; j >= 0; --j) {
-      if (j < cnt) {
-        const size_t off = (size_t)(t0 + j) * N + n;
-        const float m1 = mm[j];
+        for (int j = kL - 1; j >= 0; --j) {
+          if (j < cnt) {
+            const size_t off = (size_t)(t0 + j) * N + n;
+            const float m1 = mm[j];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
-          if (s < a.ns) {
-            const float v0 = vv[s][j], v1 = vv[s][j + 1];
-            const float delta = __fsub_rn(__fadd_rn(rr[s][j], __fmul_rn(__fmul_rn(a.gamma, v1), m1)), v0);
-            g[s] = __fadd_rn(delta, __fmul_rn(__fmul_rn(a.gl, m1), g[s]));
-            const float ret = __fadd_rn(g[s], v0);
-            a.ret[s][off] = ret;
-            a.adv[s][off] = __fsub_rn(ret, v0);
+            for (int s = 0; s < 2; ++s)
+              if (s < a.ns) {
+                const float v0 = vv[s][j], v1 = vv[s][j + 1];
+                const float delta = __fsub_rn(__fadd_rn(rr[s][j], __fmul_rn(__fmul_rn(a.gamma, v1), m1)), v0);
+                g[s] = __fadd_rn(delta, __fmul_rn(__fmul_rn(a.gl, m1), g[s]));
+                const float ret = __fadd_rn(g[s], v0);
+                a.ret[s][off] = ret;
+                a.adv[s][off] = __fsub_rn(ret, v0);
+              }
           }
+        }
+        sG[0][lane] = g[0];
+        sG[1][lane] = g[1];
       }
+      __syncthreads();
     }
   }
 }
@@ -191,9 +212,9 @@ extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* c
   a.m = masks; a.T = T; a.N = N;
   a.gamma = (float)gamma;
   a.gl = (float)(gamma * lam);
-  if (algo == 0) algo = (N >= 4096 || T < 16) ? 1 : 2;
+  if (algo == 0) algo = 1;  // the chunked march is bit-exact and parallel over both N and T
   if (algo == 1) {
-    gae_march_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(a);
+    gae_march_kernel<<<(N + 31) / 32, 32 * kW, 0, as_stream(stream)>>>(a);
   } else if (algo == 2) {
     const long long threads = (long long)N * 32;
     gae_warp_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(a);

@@ -454,6 +454,11 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 void svla_tmap_cache_free(void* cache) { delete reinterpret_cast<TmapCache*>(cache); }
 
+int svla_make_tmap_bf16(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
+                        CUtensorMap* out) {
+  return make_tmap(ctx, ptr, inner, outer, ld, bi, bo, out);
+}
+
 bool svla_gemm_tc_supported(const svla_gemm_desc* d) {
   if (d->dtypeA != SVLA_BF16 || d->dtypeB != SVLA_BF16) return false;
   if (d->transA && !d->transB) {

@@ -324,14 +324,20 @@ extern "C" int svla_rmsnorm_bwd(svla_ctx* ctx, const void* dy, int dtype_dy, con
                                 float* dw, long long rows, int D, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && dy && x && w && rstd && dx, "NULL argument");
   SVLA_CHECK_ARG(D % 128 == 0 && D <= 128 * kMaxV, "D must be a multiple of 128, <= 1024");
-  SVLA_CHECK_ARG(dtype_dx == dtype_dy, "dx and dy must share a dtype");
+  SVLA_CHECK_ARG(dtype_dx == dtype_dy || dtype_dx == SVLA_F32, "dx must be fp32 or share dy's dtype");
   if (rows <= 0) return SVLA_OK;
   const int grid = norm_grid(ctx, rows, 2);
   float* partial = reinterpret_cast<float*>(ctx->ws);
   const size_t smem = sizeof(float) * kWarps * D;
-  DISPATCH2(dtype_dy, TDY, dtype_in, TI,
-            (rmsnorm_bwd_kernel<TDY, TI, TDY><<<grid, kWarps * 32, smem, as_stream(stream)>>>(
-                (const TDY*)dy, (const TI*)x, w, rstd, (TDY*)dx, accumulate_dx, partial, rows, D)));
+  if (dtype_dx == dtype_dy) {
+    DISPATCH2(dtype_dy, TDY, dtype_in, TI,
+              (rmsnorm_bwd_kernel<TDY, TI, TDY><<<grid, kWarps * 32, smem, as_stream(stream)>>>(
+                  (const TDY*)dy, (const TI*)x, w, rstd, (TDY*)dx, accumulate_dx, partial, rows, D)));
+  } else {
+    DISPATCH2(dtype_dy, TDY, dtype_in, TI,
+              (rmsnorm_bwd_kernel<TDY, TI, float><<<grid, kWarps * 32, smem, as_stream(stream)>>>(
+                  (const TDY*)dy, (const TI*)x, w, rstd, (float*)dx, accumulate_dx, partial, rows, D)));
+  }
   SVLA_LAUNCH_CHECK();
   if (dw) {
     fold_partials_kernel<<<(D + 255) / 256, 256, 0, as_stream(stream)>>>(partial, grid, 1, D, dw, nullptr, nullptr);

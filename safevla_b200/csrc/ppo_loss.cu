@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(kRows) ppo_lag_kernel(PpoArgs a) {
   const bool has_pi = a.logits != nullptr, has_v = a.values != nullptr, has_cv = a.c_values != nullptr;
   const float pen = (a.hp.use_lagrangian && a.lambda_dev) ? *a.lambda_dev : 0.f;
   const float clip = a.hp.clip_param;
+  const bool vec4 = (A & 3) == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.dlogits) & 15) == 0;
   const float gs = a.hp.inv_count * a.hp.grad_scale;
   float acc[kNQ];
 #pragma unroll
@@ -65,26 +67,47 @@ __global__ void __launch_bounds__(kRows) ppo_lag_kernel(PpoArgs a) {
     const long long i = r0 + tid;
     const bool live = tid < rows;
     if (has_pi) {
-      // coalesced load of the [rows, A] logits tile
+      // coalesced load of the [rows, A] logits tile (128-bit when A % 4 == 0), no per-element div/mod
       const float* src = a.logits + r0 * A;
       const int cnt = rows * A;
-      for (int e = tid; e < cnt; e += kRows) tile[(e / A) * ldt + (e % A)] = __ldg(src + e);
+      if (vec4) {
+        const int A4 = A >> 2, cnt4 = cnt >> 2, dq = kRows / A4, dr = kRows % A4;
+        int row = tid / A4, c4 = tid % A4;
+        for (int e = tid; e < cnt4; e += kRows) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src) + e);
+          float* d = tile + row * ldt + c4 * 4;
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          c4 += dr; row += dq;
+          if (c4 >= A4) { c4 -= A4; ++row; }
+        }
+      } else {
+        const int dq = kRows / A, dr = kRows % A;
+        int row = tid / A, col = tid % A;
+        for (int e = tid; e < cnt; e += kRows) {
+          tile[row * ldt + col] = __ldg(src + e);
+          col += dr; row += dq;
+          if (col >= A) { col -= A; ++row; }
+        }
+      }
       __syncthreads();
       if (live) {
         float* row = tile + tid * ldt;
         float mx = -INFINITY;
         for (int k = 0; k < A; ++k) mx = fmaxf(mx, row[k]);
-        float se = 0.f;
-        for (int k = 0; k < A; ++k) se += expf(row[k] - mx);
-        const float lse = mx + logf(se);
         const int act = (int)a.actions[i];
-        const float logp_a = row[act] - lse;
-        float H = 0.f;
+        const float l_act = row[act] - mx;
+        // one exp per logit: e_k overwrites the tile; H = log(se) - sum(e_k (l_k - mx)) / se
+        float se = 0.f, sel = 0.f;
         for (int k = 0; k < A; ++k) {
-          const float lp = row[k] - lse;
-          const float p = expf(lp);
-          H -= (p > 0.f) ? p * lp : 0.f;
+          const float d = row[k] - mx;
+          const float e = expf(d);
+          se += e;
+          sel += (e > 0.f) ? e * d : 0.f;
+          row[k] = e;
         }
+        const float lse_rel = logf(se), inv_se = 1.f / se;
+        const float logp_a = l_act - lse_rel;
+        const float H = lse_rel - sel * inv_se;
         const float oldlp = a.old_logp[i];
         const float ratio = expf(logp_a - oldlp);
         const float clamped = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
@@ -103,18 +126,34 @@ __global__ void __launch_bounds__(kRows) ppo_lag_kernel(PpoArgs a) {
         const float g_lp = use_clamped ? 0.f : -(ratio * x / onep) * a.hp.w_action * gs;
         const float g_ent = a.hp.w_entropy * gs;
         for (int k = 0; k < A; ++k) {
-          const float lp = row[k] - lse;
-          const float p = expf(lp);
+          const float e = row[k];
+          const float p = e * inv_se;
           float g = g_lp * ((k == act ? 1.f : 0.f) - p);
-          if (g_ent != 0.f) g += g_ent * ((p > 0.f) ? p * (lp + H) : 0.f);
+          if (g_ent != 0.f) g += g_ent * ((e > 0.f) ? p * (logf(e) - lse_rel + H) : 0.f);
           row[k] = g;
         }
       }
       __syncthreads();
       if (a.dlogits) {
         float* dst = a.dlogits + r0 * A;
-        const int cnt2 = rows * A;
-        for (int e = tid; e < cnt2; e += kRows) dst[e] = tile[(e / A) * ldt + (e % A)];
+        if (vec4) {
+          const int A4 = A >> 2, cnt4 = cnt >> 2, dq = kRows / A4, dr = kRows % A4;
+          int row = tid / A4, c4 = tid % A4;
+          for (int e = tid; e < cnt4; e += kRows) {
+            const float* d = tile + row * ldt + c4 * 4;
+            reinterpret_cast<float4*>(dst)[e] = make_float4(d[0], d[1], d[2], d[3]);
+            c4 += dr; row += dq;
+            if (c4 >= A4) { c4 -= A4; ++row; }
+          }
+        } else {
+          const int dq = kRows / A, dr = kRows % A;
+          int row = tid / A, col = tid % A;
+          for (int e = tid; e < cnt; e += kRows) {
+            dst[e] = tile[row * ldt + col];
+            col += dr; row += dq;
+            if (col >= A) { col -= A; ++row; }
+          }
+        }
       }
       __syncthreads();
     }

@@ -276,37 +276,41 @@ class Tower:
     def decoder_fwd(self, obs_embed, prev_actions, masks, in_hand, time_step, traj_nt, perm_tn, T, N,
                     want_logits: bool, want_values: bool, keep: bool):
         """obs_embed [T*N, 512] (adt); index tensors in [T, N] order; traj_nt int64 [N, T];
-        perm_tn[t*N+n] = n*T+t.  Returns dict(logits [T,N,A], values [T,N,1]) fp32 and a stash."""
-        W, f32 = self.W, torch.float32
+        perm_tn[t*N+n] = n*T+t.  Returns dict(logits [T,N,A], values [T,N,1]) fp32 and a stash.
+        The residual stream h stays fp32; GEMM operands (normed activations, q/k/v, gate) use the
+        tower's activation dtype, so bf16 mode runs on the tcgen05 kernels."""
+        W, f32, ddt = self.W, torch.float32, self.adt
         Md = T * N
         t: Dict[str, torch.Tensor] = {}
         x = self._new(Md, D, dtype=f32)  # [N, T, D]
         ops.embed_time_fwd(obs_embed, prev_actions, masks, in_hand, time_step, W.p("last_actions_embed.weight"),
                            W.p("object_in_hand_embed.weight") if in_hand is not None else None,
                            self.div_term, x, T, N, self.A)
-        qdt = f32 if T <= 208 else torch.bfloat16  # shared-memory budget of the attention kernel
+        if ddt == f32 and T > 208:
+            raise NotImplementedError("fp32 parity mode supports T <= 208 (shared-memory attention tile)")
         h = x
         for l in range(3):
             p = f"decoder.layers.{l}."
             r1 = self._new(Md, dtype=f32)
-            y1 = ops.rmsnorm_fwd(h, W.p(p + "attention_norm.weight"), self._new(Md, D, dtype=f32), RMS_EPS, r1)
-            qkv = ops.gemm(y1, W.p(p + "attention.wq.weight", (3 * D, D), 3), self._new(Md, 3 * D, dtype=qdt))
-            ao, lse = self._new(Md, D, dtype=qdt), self._new(N * H * T, dtype=f32)
+            y1 = ops.rmsnorm_fwd(h, W.p(p + "attention_norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, r1)
+            qkv = ops.gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, 3 * D, dtype=ddt))
+            ao, lse = self._new(Md, D, dtype=ddt), self._new(N * H * T, dtype=f32)
             ops.attn_fwd(ATTN_TRAJ_CAUSAL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, lse, N, T,
                          scale=1.0 / math.sqrt(DH), traj=traj_nt)
-            h2 = ops.gemm(ao, W.w(p + "attention.wo.weight", dtype=qdt), self._new(Md, D, dtype=f32), residual=h)
+            h2 = ops.gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h)
             r2 = self._new(Md, dtype=f32)
-            y2 = ops.rmsnorm_fwd(h2, W.p(p + "ffn_norm.weight"), self._new(Md, D, dtype=f32), RMS_EPS, r2)
-            ab = ops.gemm(y2, W.p(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2), self._new(Md, 2 * DEC_FF, dtype=f32))
-            g = ops.swiglu_fwd(ab, self._new(Md, DEC_FF, dtype=f32))
-            h3 = ops.gemm(g, W.p(p + "feed_forward.w2.weight"), self._new(Md, D, dtype=f32), residual=h2)
+            y2 = ops.rmsnorm_fwd(h2, W.p(p + "ffn_norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, r2)
+            ab = ops.gemm(y2, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
+                          self._new(Md, 2 * DEC_FF, dtype=ddt))
+            g = ops.swiglu_fwd(ab, self._new(Md, DEC_FF, dtype=ddt))
+            h3 = ops.gemm(g, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h2)
             if keep:
                 t.update({f"h_{l}": h, f"r1_{l}": r1, f"y1_{l}": y1, f"qkv_{l}": qkv, f"ao_{l}": ao, f"lse_{l}": lse,
                           f"h2_{l}": h2, f"r2_{l}": r2, f"y2_{l}": y2, f"ab_{l}": ab, f"g_{l}": g})
             h = h3
         rf = self._new(Md, dtype=f32)
-        yf = ops.rmsnorm_fwd(h, W.p("decoder.norm.weight"), self._new(Md, D, dtype=f32), RMS_EPS, rf)
-        b_nt = ops.gemm(yf, W.p("decoder.output.weight"), self._new(Md, D, dtype=f32))
+        yf = ops.rmsnorm_fwd(h, W.p("decoder.norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, rf)
+        b_nt = ops.gemm(yf, W.w("decoder.output.weight", dtype=ddt), self._new(Md, D, dtype=f32))
         b_tn = ops.copy_rows(b_nt, self._new(Md, D, dtype=f32), Md, D, idx=perm_tn)
         out = {}
         if want_logits:
@@ -316,14 +320,17 @@ class Tower:
             out["values"] = ops.gemm(b_tn, W.p("critic.fc.weight"), self._new(Md, 1, dtype=f32),
                                      bias=W.p("critic.fc.bias")).view(T, N, 1)
         if keep:
-            t.update({"hf": h, "rf": rf, "yf": yf, "b_tn": b_tn, "qdt": qdt})
+            t.update({"hf": h, "rf": rf, "yf": yf, "b_tn": b_tn})
         return out, t
 
     def decoder_bwd(self, dlogits, dvalues, t, prev_actions, masks, in_hand, traj_nt, perm_nt, T, N):
         """Returns d obs_embed [T*N, 512] (adt).  perm_nt[n*T+t] = t*N+n."""
-        W, f32 = self.W, torch.float32
+        W, f32, ddt = self.W, torch.float32, self.adt
         Md = T * N
-        qdt = t["qdt"]
+
+        def operand(x):  # GEMM-operand copy of an fp32 gradient in the activation dtype
+            return x if ddt == f32 else ops.copy_rows(x, self._new(Md, D, dtype=ddt), Md, D)
+
         db_tn = None
         if dlogits is not None:
             dl = dlogits.view(Md, self.A)
@@ -336,34 +343,36 @@ class Tower:
             ops.colsum(dv, W.g("critic.fc.bias"), accumulate=True)
             db_tn = ops.gemm(dv, W.p("critic.fc.weight"), self._new(Md, D, dtype=f32), trans_b=False,
                              residual=db_tn)
-        db_nt = ops.copy_rows(db_tn, self._new(Md, D, dtype=f32), Md, D, idx=perm_nt)
+        db_nt = ops.copy_rows(db_tn, self._new(Md, D, dtype=ddt), Md, D, idx=perm_nt)
         ops.gemm(db_nt, t["yf"], W.g("decoder.output.weight"), trans_a=True, trans_b=False, accumulate=True)
-        dyf = ops.gemm(db_nt, W.p("decoder.output.weight"), self._new(Md, D, dtype=f32), trans_b=False)
+        dyf = ops.gemm(db_nt, W.w("decoder.output.weight", dtype=ddt), self._new(Md, D, dtype=ddt), trans_b=False)
         dh = ops.rmsnorm_bwd(dyf, t["hf"], W.p("decoder.norm.weight"), t["rf"], self._new(Md, D, dtype=f32),
                              W.g("decoder.norm.weight"))
         for l in (2, 1, 0):
             p = f"decoder.layers.{l}."
-            ops.gemm(dh, t[f"g_{l}"], W.g(p + "feed_forward.w2.weight"), trans_a=True, trans_b=False, accumulate=True)
-            dg = ops.gemm(dh, W.p(p + "feed_forward.w2.weight"), self._new(Md, DEC_FF, dtype=f32), trans_b=False)
-            dab = ops.swiglu_bwd(t[f"ab_{l}"], dg, self._new(Md, 2 * DEC_FF, dtype=f32))
+            dh_o = operand(dh)
+            ops.gemm(dh_o, t[f"g_{l}"], W.g(p + "feed_forward.w2.weight"), trans_a=True, trans_b=False, accumulate=True)
+            dg = ops.gemm(dh_o, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(Md, DEC_FF, dtype=ddt),
+                          trans_b=False)
+            dab = ops.swiglu_bwd(t[f"ab_{l}"], dg, self._new(Md, 2 * DEC_FF, dtype=ddt))
             ops.gemm(dab, t[f"y2_{l}"], W.g(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2), trans_a=True,
                      trans_b=False, accumulate=True)
-            dy2 = ops.gemm(dab, W.p(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2), self._new(Md, D, dtype=f32),
-                           trans_b=False)
+            dy2 = ops.gemm(dab, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
+                           self._new(Md, D, dtype=ddt), trans_b=False)
             ops.rmsnorm_bwd(dy2, t[f"h2_{l}"], W.p(p + "ffn_norm.weight"), t[f"r2_{l}"], dh,
                             W.g(p + "ffn_norm.weight"), accumulate_dx=True)  # dh := d h2
             ao = t[f"ao_{l}"]
-            dh_q = dh if qdt == f32 else ops.copy_rows(dh, self._new(Md, D, dtype=qdt), Md, D)
-            ops.gemm(dh_q, ao, W.g(p + "attention.wo.weight"), trans_a=True, trans_b=False, accumulate=True)
-            dao = ops.gemm(dh_q, W.w(p + "attention.wo.weight", dtype=qdt), self._new(Md, D, dtype=qdt), trans_b=False)
+            dh_o = operand(dh)
+            ops.gemm(dh_o, ao, W.g(p + "attention.wo.weight"), trans_a=True, trans_b=False, accumulate=True)
+            dao = ops.gemm(dh_o, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=ddt), trans_b=False)
             qkv = t[f"qkv_{l}"]
-            dqkv = self._new(Md, 3 * D, dtype=qdt)
+            dqkv = self._new(Md, 3 * D, dtype=ddt)
             ops.attn_bwd(ATTN_TRAJ_CAUSAL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, dao, dqkv[:, 0:D],
                          dqkv[:, D:2 * D], dqkv[:, 2 * D:3 * D], t[f"lse_{l}"], N, T, scale=1.0 / math.sqrt(DH),
                          traj=traj_nt)
             ops.gemm(dqkv, t[f"y1_{l}"], W.g(p + "attention.wq.weight", (3 * D, D), 3), trans_a=True, trans_b=False,
                      accumulate=True)
-            dy1 = ops.gemm(dqkv, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=qdt), self._new(Md, D, dtype=f32),
+            dy1 = ops.gemm(dqkv, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, D, dtype=ddt),
                            trans_b=False)
             ops.rmsnorm_bwd(dy1, t[f"h_{l}"], W.p(p + "attention_norm.weight"), t[f"r1_{l}"], dh,
                             W.g(p + "attention_norm.weight"), accumulate_dx=True)  # dh := d h

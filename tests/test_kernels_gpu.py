@@ -443,6 +443,36 @@ def test_gemm_tcgen05(dev, M, N, K, ta, tb):
     assert (acc.double() - exp2).abs().max().item() < 2e-5 * max(scale, 1.0) * max(1.0, (K / 512) ** 0.5)
 
 
+@pytest.mark.parametrize("mode,S,B", [(0, 117, 5), (0, 128, 2), (1, 128, 3), (1, 16, 1), (0, 33, 300)])
+def test_attention_tcgen05_vs_cuda_core(dev, mode, S, B):
+    """tcgen05 attention (forced) against the CUDA-core kernel on identical bf16 inputs, fwd and bwd."""
+    H, D = 8, 512
+    lib = _L().load_library()
+    g = torch.Generator().manual_seed(S * 7 + mode)
+    qkv = (torch.randn(B * S, 3 * D, generator=g) * 0.7).to(dev, torch.bfloat16)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    do = torch.randn(B * S, D, generator=g).to(dev, torch.bfloat16)
+    traj = torch.cumsum((torch.rand(B, S, generator=g) < 0.1).long(), 1).to(dev) if mode == 1 else None
+    res = {}
+    try:
+        for impl in (1, 2):
+            lib.svla_set_attn_impl(impl)
+            o = torch.zeros(B * S, D, device=dev, dtype=torch.bfloat16)
+            lse = torch.zeros(B * H * S, device=dev)
+            _ops().attn_fwd(mode, q, k, v, o, lse, B, S, traj=traj)
+            dqkv = torch.zeros(B * S, 3 * D, device=dev, dtype=torch.bfloat16)
+            _ops().attn_bwd(mode, q, k, v, o, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], lse, B, S, traj=traj)
+            torch.cuda.synchronize()
+            res[impl] = (o.float(), lse, dqkv.float())
+    finally:
+        lib.svla_set_attn_impl(0)
+    assert relerr(res[2][0], res[1][0]) < 2e-2, relerr(res[2][0], res[1][0])
+    assert (res[2][1] - res[1][1]).abs().max().item() < 2e-2
+    for c in range(3):
+        a, b = res[2][2][:, c * D:(c + 1) * D], res[1][2][:, c * D:(c + 1) * D]
+        assert relerr(a, b) < 4e-2, (c, relerr(a, b))
+
+
 def test_gemm_tcgen05_strided_and_repeat(dev):
     # CLS-row view (lda = S*D), column-sliced weight, repeated launches reuse cached tensor maps
     S, D, R = 117, 512, 300
