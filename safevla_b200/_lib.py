@@ -122,6 +122,58 @@ def load_library() -> C.CDLL:
     return lib
 
 
+class _Profiled:
+    """Wraps one C entry point with CUDA events on the current stream (bench/profiling only)."""
+
+    def __init__(self, name, fn, sink):
+        self.name, self.fn, self.sink = name, fn, sink
+
+    def __call__(self, *args):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = self.fn(*args)
+        e1.record()
+        self.sink.append((self.name, e0, e1))
+        return rc
+
+
+_prof_sink = None
+_SKIP_PROFILE = {"svla_ctx_create", "svla_ctx_destroy", "svla_last_error", "svla_version", "svla_sm_count",
+                 "svla_launch_count", "svla_gemm_which", "svla_set_attn_impl"}
+
+
+def profile_start():
+    """Start recording per-entry-point device time (CUDA events around every C-ABI call)."""
+    global _prof_sink
+    lib = load_library()
+    _prof_sink = []
+    for name in PROTOTYPES:
+        if name in _SKIP_PROFILE:
+            continue
+        fn = getattr(lib, name)
+        if not isinstance(fn, _Profiled):
+            setattr(lib, name, _Profiled(name, fn, _prof_sink))
+        else:
+            fn.sink = _prof_sink
+
+
+def profile_stop():
+    """Stop recording; returns {entry point: (total ms, calls)} (synchronises the device)."""
+    global _prof_sink
+    lib = load_library()
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _prof_sink or []:
+        ms, n = out.get(name, (0.0, 0))
+        out[name] = (ms + e0.elapsed_time(e1), n + 1)
+    for name in PROTOTYPES:
+        fn = getattr(lib, name, None)
+        if isinstance(fn, _Profiled):
+            setattr(lib, name, fn.fn)
+    _prof_sink = None
+    return out
+
+
 def last_error() -> str:
     return (load_library().svla_last_error() or b"").decode()
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "fold.cuh"
 
 namespace {
 
@@ -94,31 +95,44 @@ __global__ void __launch_bounds__(128) embed_time_bwd_copy_kernel(const float* _
   for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)
     store4<T>(dobs + (long long)row * D + c, *reinterpret_cast<const float4*>(src + c));
 }
+// table gradients: grid (table rows, row slices); every block walks its slice of (t, n) rows in order and writes a
+// partial; a second kernel folds the slices in order (deterministic, no atomics)
+constexpr int kEmbedSlices = 32;
 __global__ void __launch_bounds__(128) embed_table_grad_kernel(const float* __restrict__ dx,
                                                                const int64_t* __restrict__ prev,
                                                                const float* __restrict__ masks,
-                                                               const int64_t* __restrict__ in_hand, float* __restrict__ dEa,
-                                                               float* __restrict__ dEh, int T_, int N, int A, int D) {
-  // blocks [0, A+2): action table rows; [A+2, A+5): in-hand table rows
-  const int k = blockIdx.x;
+                                                               const int64_t* __restrict__ in_hand,
+                                                               float* __restrict__ partial, int T_, int N, int A, int D) {
+  // blockIdx.x in [0, A+2): action table rows; [A+2, A+5): in-hand table rows
+  const int k = blockIdx.x, slice = blockIdx.y;
   const bool is_hand = k >= A + 2;
-  if (is_hand && (in_hand == nullptr || dEh == nullptr)) return;
   const int kk = is_hand ? k - (A + 2) : k;
-  float* dst = is_hand ? dEh + (long long)kk * D : dEa + (long long)kk * D;
-  float acc[4];
-  for (int c0 = 0; c0 < D; c0 += blockDim.x * 4) {
-    const int c = c0 + threadIdx.x * 4;
-    if (c >= D) break;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    for (int row = 0; row < T_ * N; ++row) {
-      const int idx = is_hand ? (int)in_hand[row] : ((masks[row] != 0.f) ? (int)prev[row] : A);
-      if (idx != kk) continue;
-      const int t = row / N, n = row % N;
-      const float4 v = *reinterpret_cast<const float4*>(dx + ((long long)n * T_ + t) * D + c);
-      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  const int R = T_ * N, chunk = (R + kEmbedSlices - 1) / kEmbedSlices;
+  const int r0 = slice * chunk, r1 = min(R, r0 + chunk);
+  float* dst = partial + ((long long)slice * (A + 5) + k) * D;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(is_hand && in_hand == nullptr)) {
+      for (int row = r0; row < r1; ++row) {
+        const int idx = is_hand ? (int)in_hand[row] : ((masks[row] != 0.f) ? (int)prev[row] : A);
+        if (idx != kk) continue;
+        const int t = row / N, n = row % N;
+        const float4 v = *reinterpret_cast<const float4*>(dx + ((long long)n * T_ + t) * D + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
-    dst[c] += acc[0]; dst[c + 1] += acc[1]; dst[c + 2] += acc[2]; dst[c + 3] += acc[3];
+    *reinterpret_cast<float4*>(dst + c) = acc;
   }
+}
+__global__ void embed_table_fold_kernel(const float* __restrict__ partial, float* __restrict__ dEa, float* __restrict__ dEh,
+                                        int A, int D) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (A + 5) * D) return;
+  const int k = e / D, d = e % D;
+  float s = 0.f;
+  for (int sl = 0; sl < kEmbedSlices; ++sl) s += partial[(long long)sl * (A + 5) * D + e];
+  if (k < A + 2) dEa[(long long)k * D + d] += s;
+  else if (dEh) dEh[(long long)(k - (A + 2)) * D + d] += s;
 }
 
 // ---- NCHW -> token-major -----------------------------------------------------------------
@@ -341,7 +355,12 @@ extern "C" int svla_embed_time_bwd(svla_ctx* ctx, const float* dx, const int64_t
   SVLA_DISPATCH_DTYPE(dtype_out, TO, (embed_time_bwd_copy_kernel<TO><<<T * N, 128, 0, as_stream(stream)>>>(
                                          dx, (TO*)d_obs_embed, T, N, D)));
   SVLA_LAUNCH_CHECK();
-  embed_table_grad_kernel<<<A + 5, 128, 0, as_stream(stream)>>>(dx, prev_actions, masks, in_hand, dE_a, dE_h, T, N, A, D);
+  float* partial = reinterpret_cast<float*>(ctx->ws);
+  SVLA_CHECK_ARG((size_t)kEmbedSlices * (A + 5) * D * sizeof(float) <= ctx->ws_bytes, "workspace too small");
+  embed_table_grad_kernel<<<dim3(A + 5, kEmbedSlices), 128, 0, as_stream(stream)>>>(dx, prev_actions, masks, in_hand,
+                                                                                     partial, T, N, A, D);
+  SVLA_LAUNCH_CHECK();
+  embed_table_fold_kernel<<<((A + 5) * D + 255) / 256, 256, 0, as_stream(stream)>>>(partial, dE_a, dE_h, A, D);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
@@ -400,7 +419,7 @@ extern "C" int svla_colsum(svla_ctx* ctx, const void* x, int dtype, long long M,
                                       (const T*)x, M, N, ldx, chunk, partial)));
   }
   SVLA_LAUNCH_CHECK();
-  colsum_fold_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(partial, nb, N, out, accumulate);
+  svla_launch_fold(partial, nb, N, N, out, nullptr, nullptr, accumulate, as_stream(stream));
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }

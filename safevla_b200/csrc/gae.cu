@@ -27,24 +27,26 @@ struct GaeArgs {
   float gamma, gl;
 };
 
-// Block = 32 samplers (lanes, coalesced) x kW time-chunks (warps) of kL steps.  Every thread first pulls its
-// whole chunk into registers (all loads of the block in flight at once: 32 x kW x kL x 20 B), then the chunks run
-// their short dependent chains one after the other, latest first, handing g across through shared memory --
-// the exact operation order of the sequential recursion, so the result is bit-identical to it, while HBM sees
-// one fully parallel pass (20 B read + 16 B written per (t, n)).
-constexpr int kL = 16, kW = 8;
-
-__global__ void __launch_bounds__(32 * kW) gae_march_kernel(GaeArgs a) {
-  __shared__ float sG[2][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + lane;
+// Block = kNW*32 samplers (512 contiguous bytes of every row: DRAM-page friendly) x kW time-chunks of kL steps.
+// Every thread first pulls its chunk into registers (all loads of the block in flight at once), computes what does
+// not depend on g (delta_t, the coefficient gamma*lam*m_{t+1}) in parallel, then the chunks run their short
+// dependent chains one after the other, latest first, handing g across through shared memory -- the exact
+// operation order of the sequential recursion, so the result is bit-identical to it, while HBM sees one
+// parallel pass (20 B read + 16 B written per (t, n)).
+template <int kL, int kW, int kNW>
+__global__ void __launch_bounds__(32 * kW * kNW) gae_march_kernel(GaeArgs a) {
+  __shared__ float sG[2][32 * kNW];
+  const int lane = (threadIdx.x & 31) + 32 * ((threadIdx.x >> 5) % kNW), warp = (threadIdx.x >> 5) / kNW;
+  const int n = blockIdx.x * (32 * kNW) + lane;
   const bool live = n < a.N;
   const int T = a.T, N = a.N;
   if (warp == 0) {
     sG[0][lane] = 0.f;
     sG[1][lane] = 0.f;
-    if (live)
-      for (int s = 0; s < a.ns; ++s) a.ret[s][(size_t)T * N + n] = a.v[s][(size_t)T * N + n];
+    if (live) {
+      a.ret[0][(size_t)T * N + n] = a.v[0][(size_t)T * N + n];
+      if (a.ns > 1) a.ret[1][(size_t)T * N + n] = a.v[1][(size_t)T * N + n];
+    }
   }
   const int span = kL * kW;
   for (int sup = (T + span - 1) / span - 1; sup >= 0; --sup) {
@@ -71,33 +73,52 @@ __global__ void __launch_bounds__(32 * kW) gae_march_kernel(GaeArgs a) {
         for (int s = 0; s < 2; ++s)
           if (s < a.ns) vv[s][j + 1] = __ldg(a.v[s] + (size_t)(t0 + j + 1) * N + n);
       }
+    // everything that does not depend on g is done by all chunks in parallel: delta_t (in place of r_t) and
+    // the recursion coefficient gamma*lam*m_{t+1} (in place of m_{t+1})
+#pragma unroll
+    for (int j = 0; j < kL; ++j)
+      if (j < cnt) {
+        const float m1 = mm[j];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns)
+            rr[s][j] = __fsub_rn(__fadd_rn(rr[s][j], __fmul_rn(__fmul_rn(a.gamma, vv[s][j + 1]), m1)), vv[s][j]);
+        mm[j] = __fmul_rn(a.gl, m1);
+      }
     __syncthreads();  // sG initialised / handed over from the previous super-chunk
+    // the only serial part: g_t = delta_t + coef_t * g_{t+1}, two dependent roundings per step
 #pragma unroll 1
     for (int c = kW - 1; c >= 0; --c) {
       if (warp == c && cnt > 0) {
-        float g[2] = {sG[0][lane], sG[1][lane]};
+        float g0 = sG[0][lane], g1 = sG[1][lane];
 #pragma unroll
-        for (int j = kL - 1; j >= 0; --j) {
+        for (int j = kL - 1; j >= 0; --j)
           if (j < cnt) {
-            const size_t off = (size_t)(t0 + j) * N + n;
-            const float m1 = mm[j];
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-              if (s < a.ns) {
-                const float v0 = vv[s][j], v1 = vv[s][j + 1];
-                const float delta = __fsub_rn(__fadd_rn(rr[s][j], __fmul_rn(__fmul_rn(a.gamma, v1), m1)), v0);
-                g[s] = __fadd_rn(delta, __fmul_rn(__fmul_rn(a.gl, m1), g[s]));
-                const float ret = __fadd_rn(g[s], v0);
-                a.ret[s][off] = ret;
-                a.adv[s][off] = __fsub_rn(ret, v0);
-              }
+            g0 = __fadd_rn(rr[0][j], __fmul_rn(mm[j], g0));
+            rr[0][j] = g0;
+            if (a.ns > 1) {
+              g1 = __fadd_rn(rr[1][j], __fmul_rn(mm[j], g1));
+              rr[1][j] = g1;
+            }
           }
-        }
-        sG[0][lane] = g[0];
-        sG[1][lane] = g[1];
+        sG[0][lane] = g0;
+        sG[1][lane] = g1;
       }
       __syncthreads();
     }
+    // returns / advantages from the g held in registers, all chunks in parallel again
+#pragma unroll
+    for (int j = 0; j < kL; ++j)
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) {
+            const float ret = __fadd_rn(rr[s][j], vv[s][j]);
+            (s == 0 ? a.ret[0] : a.ret[1])[off] = ret;
+            (s == 0 ? a.adv[0] : a.adv[1])[off] = __fsub_rn(ret, vv[s][j]);
+          }
+      }
   }
 }
 
@@ -191,6 +212,11 @@ __global__ void __launch_bounds__(256) adv_normalize(const float* x, float* y, l
     y[i] = (x[i] - mean) * inv;
 }
 
+template <int kL, int kW, int kNW>
+void launch_march(const GaeArgs& a, cudaStream_t st) {
+  gae_march_kernel<kL, kW, kNW><<<(a.N + 32 * kNW - 1) / (32 * kNW), 32 * kW * kNW, 0, st>>>(a);
+}
+
 }  // namespace
 
 extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* costs, const float* value_preds,
@@ -214,7 +240,42 @@ extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* c
   a.gl = (float)(gamma * lam);
   if (algo == 0) algo = 1;  // the chunked march is bit-exact and parallel over both N and T
   if (algo == 1) {
-    gae_march_kernel<<<(N + 31) / 32, 32 * kW, 0, as_stream(stream)>>>(a);
+    // measured on B200 (tools/tune_gae.py): short register chunks win at large N (occupancy), long chunks at the
+    // BASELINE shapes (64 samplers: one super-chunk, two blocks)
+    if (N >= 2048) launch_march<2, 4, 4>(a, as_stream(stream));
+    else launch_march<16, 8, 1>(a, as_stream(stream));
+  } else if (algo == 11) {  // tuning variants of the same (bit-exact) kernel
+    launch_march<16, 8, 1>(a, as_stream(stream));
+  } else if (algo == 12) {
+    launch_march<8, 4, 2>(a, as_stream(stream));
+  } else if (algo == 13) {
+    launch_march<16, 2, 4>(a, as_stream(stream));
+  } else if (algo == 14) {
+    launch_march<4, 4, 4>(a, as_stream(stream));
+  } else if (algo == 15) {
+    launch_march<8, 1, 4>(a, as_stream(stream));
+  } else if (algo == 16) {
+    launch_march<8, 2, 8>(a, as_stream(stream));
+  } else if (algo == 17) {
+    launch_march<4, 1, 4>(a, as_stream(stream));
+  } else if (algo == 18) {
+    launch_march<4, 2, 4>(a, as_stream(stream));
+  } else if (algo == 19) {
+    launch_march<4, 8, 4>(a, as_stream(stream));
+  } else if (algo == 20) {
+    launch_march<2, 4, 4>(a, as_stream(stream));
+  } else if (algo == 21) {
+    launch_march<2, 8, 4>(a, as_stream(stream));
+  } else if (algo == 22) {
+    launch_march<4, 4, 8>(a, as_stream(stream));
+  } else if (algo == 23) {
+    launch_march<4, 4, 2>(a, as_stream(stream));
+  } else if (algo == 24) {
+    launch_march<2, 2, 4>(a, as_stream(stream));
+  } else if (algo == 25) {
+    launch_march<2, 1, 4>(a, as_stream(stream));
+  } else if (algo == 26) {
+    launch_march<1, 4, 4>(a, as_stream(stream));
   } else if (algo == 2) {
     const long long threads = (long long)N * 32;
     gae_warp_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(a);

@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -25,7 +26,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, kThreads = 256;
+constexpr int BM = 128, BK = 64, kThreads = 384;  // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
 
 // ---------------------------------------------------------------------------------------------- PTX
@@ -121,6 +122,8 @@ struct TcArgs {
   int epilogue, accumulate;
   float alpha;
   float* ws;
+  int tma_store;
+  int dbg;  // SVLA_TC_DBG experiments: 1 = skip the epilogue entirely, 2 = TMEM loads only (no global stores)
 };
 
 __device__ __forceinline__ float ld_elem(const void* p, int dt, long long i) {
@@ -158,10 +161,232 @@ __device__ __forceinline__ void st8(void* p, int dt, long long i, const float* v
   }
 }
 
+// ---- staged epilogue ------------------------------------------------------------------------------------
+// Each epilogue warp owns a [32 rows x 32 columns] staging tile per chunk (128 B rows for fp32, 64 B rows for
+// bf16), XOR-swizzled in 16-byte slots so both the per-lane row writes and the coalesced row reads are
+// conflict-free up to the 4-wavefront minimum.  Every global access of the epilogue (output, residual, ReLU-mask
+// operand, accumulate) is then a run of full 32-byte sectors along a row.
+constexpr int kStgBytes = 32 * 128;  // per epilogue warp
+
+template <bool F32> __device__ __forceinline__ int stg_off(int row, int slot) {
+  return F32 ? row * 128 + ((slot ^ (row & 7)) << 4) : row * 64 + ((slot ^ ((row >> 1) & 3)) << 4);
+}
+template <bool F32>
+__device__ __forceinline__ void stage_in(uint8_t* stg, const void* base, long long ld_bytes, long long col_bytes, int m0,
+                                         int M, int lane) {
+  constexpr int LPR = F32 ? 8 : 4, RPP = 32 / LPR;  // lanes per row, rows per pass
+#pragma unroll
+  for (int p = 0; p < 32 / RPP; ++p) {
+    const int row = p * RPP + lane / LPR, slot = lane % LPR;
+    if (m0 + row < M)
+      *reinterpret_cast<uint4*>(stg + stg_off<F32>(row, slot)) = __ldg(reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint8_t*>(base) + (long long)(m0 + row) * ld_bytes + col_bytes + slot * 16));
+  }
+  __syncwarp();
+}
+template <bool F32>
+__device__ __forceinline__ void stage_out(const uint8_t* stg, void* base, long long ld_bytes, long long col_bytes, int m0,
+                                          int M, int lane) {
+  constexpr int LPR = F32 ? 8 : 4, RPP = 32 / LPR;
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 32 / RPP; ++p) {
+    const int row = p * RPP + lane / LPR, slot = lane % LPR;
+    if (m0 + row < M)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(base) + (long long)(m0 + row) * ld_bytes + col_bytes +
+                                slot * 16) = *reinterpret_cast<const uint4*>(stg + stg_off<F32>(row, slot));
+  }
+  __syncwarp();
+}
+// 16-byte slot j of this lane's staged row -> floats (4 for fp32, 8 for bf16)
+template <bool F32>
+__device__ __forceinline__ void piece_load(const uint8_t* stg, int lane, int j, float* o) {
+  const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off<F32>(lane, j));
+  if (F32) {
+    o[0] = __uint_as_float(u.x); o[1] = __uint_as_float(u.y); o[2] = __uint_as_float(u.z); o[3] = __uint_as_float(u.w);
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h[e]);
+      o[2 * e] = f.x; o[2 * e + 1] = f.y;
+    }
+  }
+}
+
+// columns [c_begin, c_end) of the tile for the 32 rows starting at m0
+template <bool F32>
+__device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtensorMap* mapC, uint8_t* stg0, uint32_t taddr,
+                                                  int m0, int ntile0, int c_begin, int c_end, int sp, int lane) {
+  constexpr int EP = F32 ? 4 : 8;    // elements per 16-byte slot
+  constexpr int NS = F32 ? 8 : 4;    // slots per 32-column row
+  constexpr int ES = F32 ? 4 : 2;
+  const bool part = g.splits > 1;
+  uint8_t* Cb = part ? reinterpret_cast<uint8_t*>(g.ws + (size_t)sp * g.M * g.N) : reinterpret_cast<uint8_t*>(g.C);
+  const long long ldc_b = (part ? (long long)g.N : g.ldc) * ES;
+  // bf16 tiles are 2 KB: two staging buffers per warp, so a TMA store can still be reading one while the next
+  // chunk fills the other; fp32 tiles (4 KB) use the single buffer
+  constexpr int kBufs = F32 ? 1 : 2;
+  int chunk = 0;
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk) {
+    const int n0 = ntile0 + c0;
+    if (n0 >= g.N) break;  // warp-uniform
+    uint8_t* stg = stg0 + (kBufs == 2 ? (chunk & 1) * 2048 : 0);
+    if (g.tma_store) {  // the bulk store that last read this buffer must have finished reading it
+      if (lane == 0) {
+        if (kBufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      __syncwarp();
+    }
+    float4 bias4[8];
+    if (!part && g.bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bias4[e] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + e);
+    }
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+    tmem_wait_ld();
+    if (!part) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float x0 = __uint_as_float(r[4 * e]) * g.alpha, x1 = __uint_as_float(r[4 * e + 1]) * g.alpha;
+        float x2 = __uint_as_float(r[4 * e + 2]) * g.alpha, x3 = __uint_as_float(r[4 * e + 3]) * g.alpha;
+        if (g.bias) { x0 += bias4[e].x; x1 += bias4[e].y; x2 += bias4[e].z; x3 += bias4[e].w; }
+        if (g.epilogue == SVLA_EPI_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+        r[4 * e] = __float_as_uint(x0); r[4 * e + 1] = __float_as_uint(x1);
+        r[4 * e + 2] = __float_as_uint(x2); r[4 * e + 3] = __float_as_uint(x3);
+      }
+      if (g.epilogue == SVLA_EPI_RELU_MASK) {
+        stage_in<F32>(stg, g.aux, g.ldaux * ES, (long long)n0 * ES, m0, g.M, lane);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          float a[EP];
+          piece_load<F32>(stg, lane, j, a);
+#pragma unroll
+          for (int e = 0; e < EP; ++e)
+            if (!(a[e] > 0.f)) r[j * EP + e] = 0u;
+        }
+        __syncwarp();
+      }
+      if (g.residual) {
+        stage_in<F32>(stg, g.residual, g.ldr * ES, (long long)n0 * ES, m0, g.M, lane);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          float a[EP];
+          piece_load<F32>(stg, lane, j, a);
+#pragma unroll
+          for (int e = 0; e < EP; ++e) r[j * EP + e] = __float_as_uint(__uint_as_float(r[j * EP + e]) + a[e]);
+        }
+        __syncwarp();
+      }
+      if (g.accumulate) {
+        stage_in<F32>(stg, g.C, ldc_b, (long long)n0 * ES, m0, g.M, lane);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          float a[EP];
+          piece_load<F32>(stg, lane, j, a);
+#pragma unroll
+          for (int e = 0; e < EP; ++e) r[j * EP + e] = __float_as_uint(__uint_as_float(r[j * EP + e]) + a[e]);
+        }
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      uint4 u;
+      if (F32) {
+        u = make_uint4(r[j * 4], r[j * 4 + 1], r[j * 4 + 2], r[j * 4 + 3]);
+      } else {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          h[e] = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+      }
+      *reinterpret_cast<uint4*>(stg + stg_off<F32>(lane, j)) = u;
+    }
+    if (g.tma_store) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(mapC),
+                     "r"(smem_u32(stg)), "r"(n0), "r"(m0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      stage_out<F32>(stg, Cb, ldc_b, (long long)n0 * ES, m0, g.M, lane);
+    }
+  }
+  if (g.tma_store) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+  }
+}
+
+// generic per-thread epilogue (mixed residual / aux dtypes): thread = row, 16-byte accesses
+__device__ __forceinline__ void epilogue_direct(const TcArgs& g, uint32_t taddr, int m, bool row_ok, int ntile0,
+                                                int c_begin, int c_end, int sp) {
+#pragma unroll 1
+  for (int c = c_begin / 32; c < c_end / 32; ++c) {
+    const int n0 = ntile0 + c * 32;
+    if (n0 >= g.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_wait_ld();
+    if (!row_ok) continue;
+    if (g.splits > 1) {
+      float* dst = g.ws + ((size_t)sp * g.M + m) * g.N + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) * g.alpha;
+      if (g.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (g.epilogue == SVLA_EPI_RELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+      } else if (g.epilogue == SVLA_EPI_RELU_MASK) {
+        float a[8];
+        ld8(g.aux, g.dtypeAux, (long long)m * g.ldaux + n0 + j, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
+      }
+      if (g.residual) {
+        float a[8];
+        ld8(g.residual, g.dtypeR, (long long)m * g.ldr + n0 + j, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += a[e];
+      }
+      const long long ci = (long long)m * g.ldc + n0 + j;
+      if (g.accumulate) {
+        float a[8];
+        ld8(g.C, g.dtypeC, ci, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += a[e];
+      }
+      st8(g.C, g.dtypeC, ci, v);
+    }
+  }
+}
+
 // AMN / BMN: operand is MN-major (its M / N dimension is the contiguous one in global memory)
 template <int BN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kThreads, 1)
-svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ CUtensorMap mapC, TcArgs g) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -172,7 +397,8 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* stage_base = smem + kStages * kStageBytes;  // 8 epilogue warps x 4 KB staging (1024-byte aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + 8 * kStgBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
@@ -182,6 +408,7 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0 && elect_one()) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages; ++s) {
@@ -190,7 +417,7 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -278,7 +505,8 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   } else if (warp >= kEpiWarp0) {
     // ================================ epilogue ================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -287,64 +515,35 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const bool row_ok = m < g.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = tn * BN + c * 32;
-        if (n0 >= g.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tmem_wait_ld();
-        if (row_ok) {
-          if (g.splits > 1) {
-            float* dst = g.ws + ((size_t)sp * g.M + m) * g.N + n0;
+      if (g.dbg == 1) {
+      } else if (g.dbg == 2) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        uint32_t keep = 0;
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]) * g.alpha;
-              if (g.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (g.epilogue == SVLA_EPI_RELU) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-              } else if (g.epilogue == SVLA_EPI_RELU_MASK) {
-                float a[8];
-                ld8(g.aux, g.dtypeAux, (long long)m * g.ldaux + n0 + j, a);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
-              }
-              if (g.residual) {
-                float a[8];
-                ld8(g.residual, g.dtypeR, (long long)m * g.ldr + n0 + j, a);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += a[e];
-              }
-              const long long ci = (long long)m * g.ldc + n0 + j;
-              if (g.accumulate) {
-                float a[8];
-                ld8(g.C, g.dtypeC, ci, a);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += a[e];
-              }
-              st8(g.C, g.dtypeC, ci, v);
-            }
-          }
+          for (int e = 0; e < 32; ++e) keep ^= r[e];
         }
+        if (keep == 0x12345678u) reinterpret_cast<uint32_t*>(g.C)[0] = keep;
+      } else {
+        const bool part = g.splits > 1;
+        const int dtC = part ? (int)SVLA_F32 : g.dtypeC;
+        const bool staged = (!g.residual || g.dtypeR == dtC) && (!g.aux || g.dtypeAux == dtC);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const int cb = half * (BN / 2), ce = cb + BN / 2;
+        uint8_t* stg = stage_base + (warp - kEpiWarp0) * kStgBytes;
+        if (!staged) epilogue_direct(g, taddr, m, row_ok, tn * BN, cb, ce, sp);
+        else if (dtC == SVLA_F32) epilogue_staged_t<true>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane);
+        else epilogue_staged_t<false>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -393,15 +592,16 @@ EncodeTiledFn get_encode() {
 
 struct TmapCache {
   std::mutex mu;
-  std::map<std::tuple<const void*, long long, long long, long long, int, int>, CUtensorMap> maps;
+  std::map<std::tuple<const void*, long long, long long, long long, int, int, int>, CUtensorMap> maps;
 };
 
-// 2-D bf16 tensor map: inner (contiguous) extent, outer extent, outer stride ld (elements), box {bi, bo}
+// 2-D tensor map: inner (contiguous) extent, outer extent, outer stride ld (elements), box {bi, bo}.
+// kind 0: bf16, 128B swizzle (operands); kind 1: bf16, 64B swizzle (32-column output tiles); kind 2: fp32, 128B swizzle
 int make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
-              CUtensorMap* out) {
+              CUtensorMap* out, int kind = 0) {
   if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
   TmapCache* tc = reinterpret_cast<TmapCache*>(ctx->tmap_cache);
-  const auto key = std::make_tuple(ptr, inner, outer, ld, bi, bo);
+  const auto key = std::make_tuple(ptr, inner, outer, ld, bi, bo, kind);
   {
     std::lock_guard<std::mutex> lk(tc->mu);
     auto it = tc->maps.find(key);
@@ -416,12 +616,13 @@ int make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, 
     return SVLA_ERR_INTERNAL;
   }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (kind == 2 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)bi, (cuuint32_t)bo};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     svla_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r, ptr,
                    inner, outer, ld, bi, bo);
@@ -434,16 +635,17 @@ int make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, 
 }
 
 template <int BN, bool AMN, bool BMN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcArgs& g, int grid,
+              cudaStream_t st) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
-  constexpr size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  constexpr size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024 + 8 * kStgBytes + 512;
   auto kern = svla_gemm_tc_kernel<BN, AMN, BMN>;
   static bool attr_set = false;
   if (!attr_set) {
     SVLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, st>>>(ma, mb, g);
+  kern<<<grid, kThreads, smem, st>>>(ma, mb, mc, g);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
@@ -468,7 +670,7 @@ bool svla_gemm_tc_supported(const svla_gemm_desc* d) {
   } else {
     return false;  // MN-major A with K-major B is not needed by the towers
   }
-  if (d->M < 64 || d->N < 32 || d->N % 32 != 0 || d->K < 64) return false;
+  if (d->M < 64 || d->N < 64 || d->N % 64 != 0 || d->K < 64) return false;
   if (d->lda % 8 || d->ldb % 8 || !al16(d->A) || !al16(d->B)) return false;
   const int esC = d->dtypeC == SVLA_F32 ? 4 : 2;
   if (!al16(d->C) || (d->ldc * esC) % 16) return false;
@@ -502,6 +704,8 @@ int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   g.aux = d->aux; g.ldaux = d->ldaux; g.dtypeAux = d->dtypeAux;
   g.epilogue = d->epilogue; g.accumulate = d->accumulate; g.alpha = d->alpha;
   g.ws = reinterpret_cast<float*>(ctx->ws);
+  static const int dbg_env = getenv("SVLA_TC_DBG") ? atoi(getenv("SVLA_TC_DBG")) : 0;
+  g.dbg = dbg_env;
 
   CUtensorMap ma, mb;
   int rc;
@@ -512,15 +716,24 @@ int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   else rc = make_tmap(ctx, d->B, d->N, d->K, d->ldb, 64, BK, &mb);            // [K rows][N]  box {64, 64}
   if (rc) return rc;
 
+  // output tiles leave through TMA stores (32 x 32 boxes out of the swizzled staging tile) unless this launch
+  // writes split-K partials
+  CUtensorMap mc = ma;
+  g.tma_store = 0;
+  if (g.splits == 1) {
+    rc = make_tmap(ctx, d->C, d->N, d->M, d->ldc, 32, 32, &mc, d->dtypeC == SVLA_F32 ? 2 : 1);
+    if (rc) return rc;
+    g.tma_store = 1;
+  }
   const int grid = std::min(tiles * g.splits, ctx->sm_count);
   if (BN == 256) {
-    if (!amn && !bmn) rc = launch_tc<256, false, false>(ma, mb, g, grid, st);
-    else if (!amn && bmn) rc = launch_tc<256, false, true>(ma, mb, g, grid, st);
-    else rc = launch_tc<256, true, true>(ma, mb, g, grid, st);
+    if (!amn && !bmn) rc = launch_tc<256, false, false>(ma, mb, mc, g, grid, st);
+    else if (!amn && bmn) rc = launch_tc<256, false, true>(ma, mb, mc, g, grid, st);
+    else rc = launch_tc<256, true, true>(ma, mb, mc, g, grid, st);
   } else {
-    if (!amn && !bmn) rc = launch_tc<128, false, false>(ma, mb, g, grid, st);
-    else if (!amn && bmn) rc = launch_tc<128, false, true>(ma, mb, g, grid, st);
-    else rc = launch_tc<128, true, true>(ma, mb, g, grid, st);
+    if (!amn && !bmn) rc = launch_tc<128, false, false>(ma, mb, mc, g, grid, st);
+    else if (!amn && bmn) rc = launch_tc<128, false, true>(ma, mb, mc, g, grid, st);
+    else rc = launch_tc<128, true, true>(ma, mb, mc, g, grid, st);
   }
   if (rc) return rc;
   if (g.splits > 1) {
