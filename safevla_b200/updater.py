@@ -24,6 +24,7 @@ from . import _lib as L
 from . import ops
 from .lagrange import Lagrange
 from .model import ACTOR, COST, CRITIC, B200SafeActorCritic
+from .parallel import TAIL, allreduce_arena
 from .storage import B200RolloutStorage
 
 
@@ -54,7 +55,7 @@ class PPOLagConfig:
 
 
 class PPOLagUpdater:
-    TAIL = 64  # floats appended to the gradient arena for the packed scalar all-reduce
+    TAIL = TAIL  # floats appended to the gradient arena for the packed scalar all-reduce
 
     def __init__(self, model: B200SafeActorCritic, cfg: PPOLagConfig = PPOLagConfig(),
                  process_group: Optional[dist.ProcessGroup] = None):
@@ -132,11 +133,8 @@ class PPOLagUpdater:
         m, c = self.model, self.cfg
         n = m.layout.total
         prescale = 1.0
-        if self.world > 1:
-            if last:
-                self.comm[n:n + 2].copy_(storage.cost_sum_cnt)
-            dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=self.pg)  # the one collective per step
-            prescale = 1.0 / self.world
+        if self.world > 1:  # the one collective per step
+            prescale = allreduce_arena(self.comm, n, storage.cost_sum_cnt if last else None, self.pg)
         self.adam_step += 1
         hp = L.AdamHparams(c.lr, c.betas[0], c.betas[1], c.eps, c.max_grad_norm, prescale, self.adam_step, 1)
         # torch.optim.Adam skips parameters whose .grad is None: only the towers this stage trains are
