@@ -145,6 +145,10 @@ __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* 
 }
 
 // ------------------------------------------------------------------------------------------ forward
+// Shared memory per CTA: Q | K | V (3 x 16 KB); once S = Q K^T has retired, Q|K are dead and P (32 KB) is written
+// over them.  TMEM: 128 columns -- S, then O reuses columns [0, 64).  48.6 KB + 128 columns => 4 CTAs per SM, whose
+// load / MMA / softmax phases overlap each other.
+template <int MODE>
 __global__ void __launch_bounds__(128)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                    const __grid_constant__ CUtensorMap mv, AttnTcArgs a) {
@@ -153,12 +157,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
   uint8_t* sQ = smem;             // 16 KB each
   uint8_t* sK = smem + 16384;
   uint8_t* sV = smem + 32768;
-  uint8_t* sP = smem + 49152;     // 32 KB
-  int* sTraj = reinterpret_cast<int*>(smem + 81920);                       // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + 512);        // load, mma
+  uint8_t* sP = smem;             // 32 KB, aliases Q|K
+  int* sTraj = reinterpret_cast<int*>(smem + 49152);                       // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152 + 512);        // load, mma
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr uint32_t kCols = 256;  // S: [0,128), O: [128,192)
+  constexpr uint32_t kCols = 128;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -186,7 +190,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
       tma_load_2d(sK, &mk, &bars[0], h * DH, row0);
       tma_load_2d(sV, &mv, &bars[0], h * DH, row0);
     }
-    if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) sTraj[tid] = (tid < S) ? (int)a.traj[row0 + tid] : -1 - tid;
+    if (MODE == SVLA_ATTN_TRAJ_CAUSAL) sTraj[tid] = (tid < S) ? (int)a.traj[row0 + tid] : -1 - tid;
     mbar_wait(&bars[0], ph_load);
     ph_load ^= 1;
     if (tid == 0) {
@@ -198,12 +202,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
       umma_commit(&bars[1]);
     }
     __syncthreads();  // sTraj visible
-    mbar_wait(&bars[1], ph_mma);
+    mbar_wait(&bars[1], ph_mma);  // S complete: Q and K are dead from here on
     ph_mma ^= 1;
     tc_fence_after();
     // ---- softmax of row i = tid
     const int i = tid;
-    const int my_traj = (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ? sTraj[i] : 0;
+    const int my_traj = (MODE == SVLA_ATTN_TRAJ_CAUSAL) ? sTraj[i] : 0;
     float mx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -215,7 +219,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
       for (int j = 0; j < 32; ++j) {
         const int col = c * 32 + j;
         bool ok = col < S;
-        if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
+        if (MODE == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
         if (ok) mx = fmaxf(mx, __uint_as_float(r[j]));
       }
     }
@@ -235,7 +239,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
         for (int e = 0; e < 8; ++e) {
           const int col = c * 32 + j8 * 8 + e;
           bool ok = col < S && i < S;
-          if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
+          if (MODE == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
           p[e] = ok ? exp2f(__uint_as_float(r[j8 * 8 + e]) * sl2 - mxs) : 0.f;
           sum += p[e];
         }
@@ -244,13 +248,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // P complete, every thread is done reading S
     if (tid == 0) {
       tc_fence_after();
       const uint32_t p = smem_u32(sP), v = smem_u32(sV);
 #pragma unroll
-      for (int kk = 0; kk < TS / 16; ++kk)
-        umma_bf16(tmem + 128, desc_p_kmajor(p, kk), desc_mnmajor64(v, kk), idesc(128, 64, false, true), kk > 0);
+      for (int kk = 0; kk < TS / 16; ++kk)  // O overwrites TMEM columns [0, 64)
+        umma_bf16(tmem, desc_p_kmajor(p, kk), desc_mnmajor64(v, kk), idesc(128, 64, false, true), kk > 0);
       umma_commit(&bars[1]);
     }
     mbar_wait(&bars[1], ph_mma);
@@ -258,8 +262,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
     tc_fence_after();
     {
       uint32_t r0[32], r1[32];
-      tmem_ld32(tmem + lane_base + 128, r0);
-      tmem_ld32(tmem + lane_base + 160, r1);
+      tmem_ld32(tmem + lane_base, r0);
+      tmem_ld32(tmem + lane_base + 32, r1);
       tmem_wait_ld();
       if (i < S) {
         store_row64(a.o + (long long)(row0 + i) * a.ldo + h * DH, r0, r1, 1.f / sum);
@@ -278,6 +282,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ backward
+// Shared memory per CTA: Q | K | V | dO (4 x 16 KB) + ONE 32 KB tile that first holds P (for dV = P^T dO) and then,
+// once that GEMM has retired, dS (for dK = dS^T Q and dQ = dS K); dS waits in registers (packed bf16) meanwhile.
+// TMEM: S [0,128) and dP [128,256) are consumed into P/dS before dV [0,64), dK [64,128), dQ [128,192) reuse
+// their columns.  96.6 KB + 256 columns => 2 CTAs per SM.
+template <int MODE>
 __global__ void __launch_bounds__(128)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                    const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo, AttnTcArgs a) {
@@ -287,13 +296,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
   uint8_t* sK = smem + 16384;
   uint8_t* sV = smem + 32768;
   uint8_t* sdO = smem + 49152;
-  uint8_t* sP = smem + 65536;    // 32 KB
-  uint8_t* sdS = smem + 98304;   // 32 KB
-  int* sTraj = reinterpret_cast<int*>(smem + 131072);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 131072 + 512);
+  uint8_t* sP = smem + 65536;    // 32 KB: P, then dS
+  int* sTraj = reinterpret_cast<int*>(smem + 98304);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304 + 512);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
-  constexpr uint32_t kCols = 512;  // S [0,128) dP [128,256) dV [256,320) dK [320,384) dQ [384,448)
+  constexpr uint32_t kCols = 256;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -323,7 +331,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
       tma_load_2d(sV, &mv, &bars[0], h * DH, row0);
       tma_load_2d(sdO, &mdo, &bars[0], h * DH, row0);
     }
-    if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) sTraj[tid] = (tid < S) ? (int)a.traj[row0 + tid] : -1 - tid;
+    if (MODE == SVLA_ATTN_TRAJ_CAUSAL) sTraj[tid] = (tid < S) ? (int)a.traj[row0 + tid] : -1 - tid;
     // delta_i = dO_i . O_i and lse_i straight from global memory (overlaps the TMA)
     float delta = 0.f, lse2 = 0.f;
     if (i < S) {
@@ -360,8 +368,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
     mbar_wait(&bars[1], ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
-    const int my_traj = (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ? sTraj[i] : 0;
-#pragma unroll 1
+    const int my_traj = (MODE == SVLA_ATTN_TRAJ_CAUSAL) ? sTraj[i] : 0;
+    uint32_t dsp[64];  // this row's dS, packed bf16x2
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t rs[32], rp[32];
       if (c * 32 < S) {
@@ -376,29 +385,50 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
         for (int e = 0; e < 8; ++e) {
           const int col = c * 32 + j8 * 8 + e;
           bool ok = col < S && i < S;
-          if (a.mode == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
+          if (MODE == SVLA_ATTN_TRAJ_CAUSAL) ok = ok && col <= i && sTraj[col] == my_traj;
           p[e] = ok ? exp2f(__uint_as_float(rs[j8 * 8 + e]) * sl2 - lse2) : 0.f;
           ds[e] = ok ? p[e] * (__uint_as_float(rp[j8 * 8 + e]) - delta) : 0.f;
         }
         store_p8(sP, i, c * 4 + j8, p);
-        store_p8(sdS, i, c * 4 + j8, ds);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 hb = __floats2bfloat162_rn(ds[2 * e], ds[2 * e + 1]);
+          dsp[(c * 4 + j8) * 4 + e] = *reinterpret_cast<const uint32_t*>(&hb);
+        }
       }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();  // P complete; S and dP fully consumed
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t d = smem_u32(sdO), p = smem_u32(sP);
+#pragma unroll
+      for (int kk = 0; kk < TS / 16; ++kk)  // dV[keys, dh] = P^T dO  -> TMEM [0, 64)
+        umma_bf16(tmem, desc_p_mnmajor(p, kk), desc_mnmajor64(d, kk), idesc(128, 64, true, true), kk > 0);
+      umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], ph_mma);  // dV retired: the tile may now take dS
+    ph_mma ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c8 = 0; c8 < 16; ++c8) {
+      const int chunk = c8 >> 3, cc = c8 & 7;
+      *reinterpret_cast<uint4*>(sP + chunk * 16384 + i * 128 + ((cc ^ (i & 7)) << 4)) =
+          make_uint4(dsp[c8 * 4], dsp[c8 * 4 + 1], dsp[c8 * 4 + 2], dsp[c8 * 4 + 3]);
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t q = smem_u32(sQ), k = smem_u32(sK), d = smem_u32(sdO), p = smem_u32(sP), s = smem_u32(sdS);
+      const uint32_t q = smem_u32(sQ), k = smem_u32(sK), s_ = smem_u32(sP);
 #pragma unroll
-      for (int kk = 0; kk < TS / 16; ++kk)  // dV[keys, dh] = P^T dO
-        umma_bf16(tmem + 256, desc_p_mnmajor(p, kk), desc_mnmajor64(d, kk), idesc(128, 64, true, true), kk > 0);
+      for (int kk = 0; kk < TS / 16; ++kk)  // dK[keys, dh] = dS^T Q -> TMEM [64, 128)
+        umma_bf16(tmem + 64, desc_p_mnmajor(s_, kk), desc_mnmajor64(q, kk), idesc(128, 64, true, true), kk > 0);
 #pragma unroll
-      for (int kk = 0; kk < TS / 16; ++kk)  // dK[keys, dh] = dS^T Q
-        umma_bf16(tmem + 320, desc_p_mnmajor(s, kk), desc_mnmajor64(q, kk), idesc(128, 64, true, true), kk > 0);
-#pragma unroll
-      for (int kk = 0; kk < TS / 16; ++kk)  // dQ[queries, dh] = dS K
-        umma_bf16(tmem + 384, desc_p_kmajor(s, kk), desc_mnmajor64(k, kk), idesc(128, 64, false, true), kk > 0);
+      for (int kk = 0; kk < TS / 16; ++kk)  // dQ[queries, dh] = dS K -> TMEM [128, 192)
+        umma_bf16(tmem + 128, desc_p_kmajor(s_, kk), desc_mnmajor64(k, kk), idesc(128, 64, false, true), kk > 0);
       umma_commit(&bars[1]);
     }
     mbar_wait(&bars[1], ph_mma);
@@ -407,16 +437,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
     {
       uint32_t r0[32], r1[32];
       const long long orow = (long long)(row0 + i) * a.ldd + h * DH;
-      tmem_ld32(tmem + lane_base + 256, r0);
-      tmem_ld32(tmem + lane_base + 288, r1);
+      tmem_ld32(tmem + lane_base, r0);
+      tmem_ld32(tmem + lane_base + 32, r1);
       tmem_wait_ld();
       if (i < S) store_row64(a.dv + orow, r0, r1, 1.f);
-      tmem_ld32(tmem + lane_base + 320, r0);
-      tmem_ld32(tmem + lane_base + 352, r1);
+      tmem_ld32(tmem + lane_base + 64, r0);
+      tmem_ld32(tmem + lane_base + 96, r1);
       tmem_wait_ld();
       if (i < S) store_row64(a.dk + orow, r0, r1, a.scale);
-      tmem_ld32(tmem + lane_base + 384, r0);
-      tmem_ld32(tmem + lane_base + 416, r1);
+      tmem_ld32(tmem + lane_base + 128, r0);
+      tmem_ld32(tmem + lane_base + 160, r1);
       tmem_wait_ld();
       if (i < S) store_row64(a.dq + orow, r0, r1, a.scale);
     }
@@ -452,14 +482,18 @@ int svla_attn_tc_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
   AttnTcArgs a{};
   a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = lse;
   a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo;
-  constexpr size_t smem = 81920 + 512 + 64 + 1024;
+  constexpr size_t smem = 49152 + 512 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
-    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<SVLA_ATTN_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<SVLA_ATTN_TRAJ_CAUSAL>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const int grid = std::min(B * H, 2 * ctx->sm_count);
-  attn_tc_fwd_kernel<<<grid, 128, smem, st>>>(mq, mk, mv, a);
+  const int grid = std::min(B * H, 4 * ctx->sm_count);
+  if (mode == SVLA_ATTN_FULL) attn_tc_fwd_kernel<SVLA_ATTN_FULL><<<grid, 128, smem, st>>>(mq, mk, mv, a);
+  else attn_tc_fwd_kernel<SVLA_ATTN_TRAJ_CAUSAL><<<grid, 128, smem, st>>>(mq, mk, mv, a);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
@@ -479,14 +513,18 @@ int svla_attn_tc_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
   a.o_in = reinterpret_cast<const __nv_bfloat16*>(o); a.d_o = reinterpret_cast<const __nv_bfloat16*>(d_o); a.ldo = ldo;
   a.dq = reinterpret_cast<__nv_bfloat16*>(dq); a.dk = reinterpret_cast<__nv_bfloat16*>(dk);
   a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.ldd = ldd;
-  constexpr size_t smem = 131072 + 512 + 64 + 1024;
+  constexpr size_t smem = 98304 + 512 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
-    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<SVLA_ATTN_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<SVLA_ATTN_TRAJ_CAUSAL>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const int grid = std::min(B * H, ctx->sm_count);
-  attn_tc_bwd_kernel<<<grid, 128, smem, st>>>(mq, mk, mv, mdo, a);
+  const int grid = std::min(B * H, 2 * ctx->sm_count);
+  if (mode == SVLA_ATTN_FULL) attn_tc_bwd_kernel<SVLA_ATTN_FULL><<<grid, 128, smem, st>>>(mq, mk, mv, mdo, a);
+  else attn_tc_bwd_kernel<SVLA_ATTN_TRAJ_CAUSAL><<<grid, 128, smem, st>>>(mq, mk, mv, mdo, a);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
