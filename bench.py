@@ -51,6 +51,19 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/): one representative
+    launch (the FFN-up forward GEMM of a 1024-row chunk), next to its algorithmic bytes."""
+    p = os.path.join(ROOT, "profiles", "ncu_r01_traffic.json")
+    if not os.path.exists(p):
+        return {"traffic": None}
+    d = json.load(open(p)).get("svla_gemm_tc2_kernel<0, 0>")
+    if not d:
+        return {"traffic": None}
+    return {"traffic": d["dram_bytes"], "traffic_launch": d["shape"], "traffic_algorithmic_bytes": d["algorithmic_bytes"],
+            "traffic_src": "profiles/ncu_r01.md"}
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -288,6 +301,7 @@ def run_b200(args, wl, name):
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "launches_per_step": rec["n"] // args.steps,
                 "share_of_step": rec["ms"] * 1e-3 / (t_res * args.steps), "peak_src": pk["src"] + " (sustained bf16)"}
+        roof.update(ncu_traffic())
     step_tf = value * wl["gflop_per_sample"] / 1e3
     line = {
         "metric": "ppo_lagrangian_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,

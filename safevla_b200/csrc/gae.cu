@@ -122,6 +122,126 @@ __global__ void __launch_bounds__(32 * kW * kNW) gae_march_kernel(GaeArgs a) {
   }
 }
 
+// ---- 128-bit variant of the march: every lane owns FOUR adjacent samplers --------------------------------------
+// Same schedule and the same per-sampler operation order as gae_march_kernel (bit-exact), but every global access is
+// a 16-byte vector (a warp covers 512 contiguous bytes of a row), a quarter of the load/store instructions and
+// address arithmetic per byte.  Needs N % 4 == 0 and 16-byte aligned buffers.
+struct F4 {
+  float f[4];
+};
+__device__ __forceinline__ F4 ldg4(const float* p) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  F4 o;
+  o.f[0] = t.x; o.f[1] = t.y; o.f[2] = t.z; o.f[3] = t.w;
+  return o;
+}
+__device__ __forceinline__ void stg4(float* p, const F4& v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v.f[0], v.f[1], v.f[2], v.f[3]);
+}
+
+template <int kL, int kW, int kNW>
+__global__ void __launch_bounds__(32 * kW * kNW) gae_march4_kernel(GaeArgs a) {
+  __shared__ float4 sG[2][32 * kNW];
+  const int lane = (threadIdx.x & 31) + 32 * ((threadIdx.x >> 5) % kNW), warp = (threadIdx.x >> 5) / kNW;
+  const int n = (blockIdx.x * (32 * kNW) + lane) * 4;
+  const bool live = n < a.N;
+  const int T = a.T, N = a.N;
+  if (warp == 0) {
+    sG[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sG[1][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      stg4(a.ret[0] + (size_t)T * N + n, ldg4(a.v[0] + (size_t)T * N + n));
+      if (a.ns > 1) stg4(a.ret[1] + (size_t)T * N + n, ldg4(a.v[1] + (size_t)T * N + n));
+    }
+  }
+  const int span = kL * kW;
+  for (int sup = (T + span - 1) / span - 1; sup >= 0; --sup) {
+    const int t0 = sup * span + warp * kL;
+    const int cnt = live ? max(0, min(kL, T - t0)) : 0;
+    F4 rr[2][kL], vv[2][kL + 1], mm[kL];
+#pragma unroll
+    for (int j = 0; j < kL; ++j) {
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+        mm[j] = ldg4(a.m + off + N);  // m_{t+1}
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) {
+            rr[s][j] = ldg4(a.r[s] + off);
+            vv[s][j] = ldg4(a.v[s] + off);
+          }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kL; ++j)  // V_{t+1} of the chunk's last step
+      if (j == cnt - 1) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) vv[s][j + 1] = ldg4(a.v[s] + (size_t)(t0 + j + 1) * N + n);
+      }
+#pragma unroll
+    for (int j = 0; j < kL; ++j)
+      if (j < cnt) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float m1 = mm[j].f[k];
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            if (s < a.ns)
+              rr[s][j].f[k] = __fsub_rn(__fadd_rn(rr[s][j].f[k], __fmul_rn(__fmul_rn(a.gamma, vv[s][j + 1].f[k]), m1)),
+                                        vv[s][j].f[k]);
+          mm[j].f[k] = __fmul_rn(a.gl, m1);
+        }
+      }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = kW - 1; c >= 0; --c) {
+      if (warp == c && cnt > 0) {
+        const float4 t0v = sG[0][lane], t1v = sG[1][lane];
+        float g0[4] = {t0v.x, t0v.y, t0v.z, t0v.w}, g1[4] = {t1v.x, t1v.y, t1v.z, t1v.w};
+#pragma unroll
+        for (int j = kL - 1; j >= 0; --j)
+          if (j < cnt) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              g0[k] = __fadd_rn(rr[0][j].f[k], __fmul_rn(mm[j].f[k], g0[k]));
+              rr[0][j].f[k] = g0[k];
+              if (a.ns > 1) {
+                g1[k] = __fadd_rn(rr[1][j].f[k], __fmul_rn(mm[j].f[k], g1[k]));
+                rr[1][j].f[k] = g1[k];
+              }
+            }
+          }
+        sG[0][lane] = make_float4(g0[0], g0[1], g0[2], g0[3]);
+        sG[1][lane] = make_float4(g1[0], g1[1], g1[2], g1[3]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < kL; ++j)
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (s < a.ns) {
+            F4 ret, adv;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ret.f[k] = __fadd_rn(rr[s][j].f[k], vv[s][j].f[k]);
+              adv.f[k] = __fsub_rn(ret.f[k], vv[s][j].f[k]);
+            }
+            stg4((s == 0 ? a.ret[0] : a.ret[1]) + off, ret);
+            stg4((s == 0 ? a.adv[0] : a.adv[1]) + off, adv);
+          }
+      }
+  }
+}
+
+template <int kL, int kW, int kNW>
+void launch_march4(const GaeArgs& a, cudaStream_t st) {
+  gae_march4_kernel<kL, kW, kNW><<<(a.N / 4 + 32 * kNW - 1) / (32 * kNW), 32 * kW * kNW, 0, st>>>(a);
+}
+
 // warp per sampler; lane owns steps [lane*L, lane*L+L)
 __global__ void __launch_bounds__(128) gae_warp_scan_kernel(GaeArgs a) {
   const int lane = threadIdx.x & 31;
@@ -238,11 +358,15 @@ extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* c
   a.m = masks; a.T = T; a.N = N;
   a.gamma = (float)gamma;
   a.gl = (float)(gamma * lam);
-  if (algo == 0) algo = 1;  // the chunked march is bit-exact and parallel over both N and T
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec_ok = N % 4 == 0 && al16(rewards) && al16(value_preds) && al16(masks) && al16(returns) && al16(adv) &&
+                      (!costs || (al16(costs) && al16(c_value_preds) && al16(c_returns) && al16(c_adv)));
+  if (algo == 0 || (algo >= 40 && algo < 50 && !vec_ok)) algo = 1;  // the chunked march is bit-exact and parallel over both N and T
   if (algo == 1) {
     // measured on B200 (tools/tune_gae.py): short register chunks win at large N (occupancy), long chunks at the
     // BASELINE shapes (64 samplers: one super-chunk, two blocks)
-    if (N >= 2048) launch_march<2, 4, 4>(a, as_stream(stream));
+    if (N >= 8192 && vec_ok) launch_march4<1, 8, 1>(a, as_stream(stream));
+    else if (N >= 2048) launch_march<2, 4, 4>(a, as_stream(stream));
     else launch_march<16, 8, 1>(a, as_stream(stream));
   } else if (algo == 11) {  // tuning variants of the same (bit-exact) kernel
     launch_march<16, 8, 1>(a, as_stream(stream));
@@ -276,6 +400,19 @@ extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* c
     launch_march<2, 1, 4>(a, as_stream(stream));
   } else if (algo == 26) {
     launch_march<1, 4, 4>(a, as_stream(stream));
+  } else if (algo >= 40 && algo < 50 && vec_ok) {
+    switch (algo) {
+      case 40: launch_march4<2, 4, 2>(a, as_stream(stream)); break;
+      case 41: launch_march4<2, 4, 1>(a, as_stream(stream)); break;
+      case 42: launch_march4<4, 4, 1>(a, as_stream(stream)); break;
+      case 43: launch_march4<1, 16, 2>(a, as_stream(stream)); break;
+      case 44: launch_march4<2, 8, 1>(a, as_stream(stream)); break;
+      case 45: launch_march4<1, 8, 1>(a, as_stream(stream)); break;
+      case 46: launch_march4<1, 8, 2>(a, as_stream(stream)); break;
+      case 47: launch_march4<1, 16, 1>(a, as_stream(stream)); break;
+      case 48: launch_march4<1, 4, 1>(a, as_stream(stream)); break;
+      default: launch_march4<1, 4, 2>(a, as_stream(stream)); break;
+    }
   } else if (algo == 2) {
     const long long threads = (long long)N * 32;
     gae_warp_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(a);
