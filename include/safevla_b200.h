@@ -152,6 +152,8 @@ typedef struct {
   int accumulate;                   /* C += result (C must be fp32) */
   float alpha;                      /* scales acc before bias */
   int impl;                         /* 0 auto, 1 SIMT fp32-FMA, 2 tcgen05 (bf16 operands) */
+  float* colsum_a;                  /* transA only (weight gradients, A = dY stored [K, M]): colsum_a[m] += sum_k A[k, m],
+                                       the bias gradient of the same nn.Linear; NULL = not wanted */
 } svla_gemm_desc;
 
 /* C = epi(alpha * op(A) op(B) + bias) [+ residual] -- every nn.Linear / 1x1 Conv2d forward, dgrad

@@ -45,7 +45,8 @@ class GemmDesc(C.Structure):
                 ("bias", c_p),
                 ("residual", c_p), ("ldr", c_ll), ("dtypeR", C.c_int),
                 ("aux", c_p), ("ldaux", c_ll), ("dtypeAux", C.c_int),
-                ("epilogue", C.c_int), ("accumulate", C.c_int), ("alpha", C.c_float), ("impl", C.c_int)]
+                ("epilogue", C.c_int), ("accumulate", C.c_int), ("alpha", C.c_float), ("impl", C.c_int),
+                ("colsum_a", c_p)]
 
 
 class RowMap(C.Structure):

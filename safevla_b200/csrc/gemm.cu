@@ -5,6 +5,7 @@
 int svla_gemm_simt(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st);
 int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st);  // returns SVLA_ERR_BAD_SHAPE if it declines
 bool svla_gemm_tc_supported(const svla_gemm_desc* d);
+bool svla_gemm_tc_fuses_colsum(const svla_gemm_desc* d);
 
 extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && d, "NULL ctx/desc");
@@ -15,8 +16,18 @@ extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream str
   SVLA_CHECK_ARG(d->lda >= (d->transA ? d->M : d->K), "lda too small");
   SVLA_CHECK_ARG(d->ldb >= (d->transB ? d->K : d->N), "ldb too small");
   SVLA_CHECK_ARG(d->ldc >= d->N, "ldc too small");
+  SVLA_CHECK_ARG(!d->colsum_a || d->transA, "colsum_a needs transA (A stored [K, M])");
   if (d->M == 0 || d->N == 0) return SVLA_OK;
   const cudaStream_t st = as_stream(stream);
+  if (d->colsum_a) {
+    // bias gradient: produced by the tensor-core weight-gradient kernel itself when that path runs, else one extra pass
+    if (d->impl != 1 && svla_gemm_tc_fuses_colsum(d)) return svla_gemm_tc(ctx, d, st);
+    svla_gemm_desc e = *d;
+    e.colsum_a = nullptr;
+    const int rc = svla_gemm(ctx, &e, stream);
+    if (rc) return rc;
+    return svla_colsum(ctx, d->A, d->dtypeA, d->K, d->M, d->lda, d->colsum_a, 1, stream);
+  }
   if (d->impl == 2) {
     if (!svla_gemm_tc_supported(d)) {
       svla_set_error("svla_gemm: impl=tcgen05 requested for an unsupported shape/dtype (M=%d N=%d K=%d)", d->M, d->N,

@@ -332,9 +332,18 @@ bool svla_gemm_tc_supported(const svla_gemm_desc* d) {
   return true;
 }
 
+static bool use_tc2() {
+  static const int v = getenv("SVLA_TC2") ? atoi(getenv("SVLA_TC2")) : 1;
+  return v != 0;
+}
+
+// true when svla_gemm_tc produces d->colsum_a itself (pair kernel, weight-gradient operand layout)
+bool svla_gemm_tc_fuses_colsum(const svla_gemm_desc* d) {
+  return d->colsum_a && d->transA && !d->transB && use_tc2() && svla_gemm_tc_supported(d) && svla_gemm_tc2_supported(d);
+}
+
 int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
-  static const int use_tc2 = getenv("SVLA_TC2") ? atoi(getenv("SVLA_TC2")) : 1;
-  if (use_tc2 && svla_gemm_tc2_supported(d)) return svla_gemm_tc2(ctx, d, st);
+  if (use_tc2() && svla_gemm_tc2_supported(d)) return svla_gemm_tc2(ctx, d, st);
   const bool amn = d->transA != 0, bmn = d->transB == 0;
   const int BN = (d->N >= 256) ? 256 : 128;
   TcArgs g;
@@ -358,6 +367,7 @@ int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   g.aux = d->aux; g.ldaux = d->ldaux; g.dtypeAux = d->dtypeAux;
   g.epilogue = d->epilogue; g.accumulate = d->accumulate; g.alpha = d->alpha;
   g.ws = reinterpret_cast<float*>(ctx->ws);
+  g.asum = nullptr; g.asum_ws = nullptr;
   static const int dbg_env = getenv("SVLA_TC_DBG") ? atoi(getenv("SVLA_TC_DBG")) : 0;
   g.dbg = dbg_env;
 

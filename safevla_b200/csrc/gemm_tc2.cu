@@ -60,7 +60,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
 
-template <bool AMN, bool BMN>
+// ASUM (weight-gradient launches, A = dY stored [rows, N_out]): the kernel also produces the bias gradient
+// asum[m] += sum_k A^T[m, k] on the tensor cores -- for the tn == 0 tile of every row block one extra N = 16 MMA per
+// k-step multiplies the same A tile with a shared-memory tile of ones into 16 spare TMEM columns.  It replaces a
+// separate pass over dY (svla_colsum).  These launches run 5 pipeline stages (the sixth slot holds the ones) and a
+// single accumulator stage (a weight gradient has at most a couple of tiles per CTA pair: nothing to overlap).
+template <bool AMN, bool BMN, bool ASUM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const __grid_constant__ CUtensorMap mapC, TcArgs g) {
@@ -70,6 +75,11 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // instruction descriptor: D=f32, A=B=bf16, majors, N=256, M=256 (pair)
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
                               ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t kIdescOnes = (1u << 4) | (1u << 7) | (1u << 10) | ((AMN ? 1u : 0u) << 15) |
+                                  ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr int kNS = ASUM ? kStages2 - 1 : kStages2;  // pipeline stages in use
+  constexpr int kAcc = ASUM ? 1 : 2;                   // accumulator stages in use
+  constexpr uint32_t kSumCol = BN2;                    // TMEM column of the ones-product (ASUM)
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -98,6 +108,11 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps of each CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (ASUM && warp == 3) {  // [8 rows x 64] bf16 ones: this CTA's half of the N = 16 operand (any layout: all ones)
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + kNS * kStageBytes);
+    for (int i = lane; i < 256; i += 32) ones[i] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
@@ -143,7 +158,7 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             for (int j = 0; j < (BN2 / 2) / 64; ++j)
               tma_load_2d_2sm(sb + j * (BK * 128), &mapB, &full_bar[stage], nrow + j * 64, kb * BK);
           }
-          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+          if (++stage == kNS) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -155,6 +170,7 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     uint32_t acc_phase = 0;
     for (int w = cluster_id; w < total_work; w += num_clusters) {
       const int sp = w / (g.tiles_n * tiles_m2);
+      const bool do_sum = ASUM && g.asum != nullptr && (w % g.tiles_n) == 0;
       const int kb0 = sp * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // both CTAs have drained this accumulator
       tc_fence_after();
@@ -171,15 +187,23 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const uint64_t db = BMN ? umma_desc(sb + k * 2048, BK * 128, 1024) : umma_desc(sb + k * 32, 16, 1024);
             umma_bf16_2sm(tmem_d, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
+          if (do_sum) {
+            const uint64_t dones = umma_desc(smem_u32(smem + kNS * kStageBytes), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = AMN ? umma_desc(sa + k * 2048, BK * 128, 1024) : umma_desc(sa + k * 32, 16, 1024);
+              umma_bf16_2sm(tmem_base + kSumCol, da, dones, kIdescOnes, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
         }
         __syncwarp();
         if (elect_one()) umma_commit_2sm(&empty_bar[stage]);
         __syncwarp();
-        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        if (++stage == kNS) { stage = 0; phase ^= 1; }
       }
       if (elect_one()) umma_commit_2sm(&tfull_bar[acc]);
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
@@ -204,11 +228,20 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (!staged) epilogue_direct(g, taddr, m, row_ok, tn * BN2, cb, ce, sp);
         else if (dtC == SVLA_F32) epilogue_staged_t<true>(g, &mapC, stg, taddr, m0, tn * BN2, cb, ce, sp, lane);
         else epilogue_staged_t<false>(g, &mapC, stg, taddr, m0, tn * BN2, cb, ce, sp, lane);
+        if (ASUM && g.asum != nullptr && tn == 0 && half == 0) {  // every column of the ones-product is the row sum
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kSumCol, r);
+          tmem_wait_ld();
+          if (row_ok) {
+            if (part) g.asum_ws[(size_t)sp * g.M + m] = __uint_as_float(r[0]);
+            else g.asum[m] += __uint_as_float(r[0]);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -222,6 +255,13 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
 __global__ void __launch_bounds__(256) tc2_splitk_reduce_kernel(TcArgs g) {
   const long long total = (long long)g.M * g.N;
+  if (g.asum) {
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < g.M; m += (long long)gridDim.x * blockDim.x) {
+      float v = 0.f;
+      for (int s = 0; s < g.splits; ++s) v += g.asum_ws[(size_t)s * g.M + m];
+      g.asum[m] += v;
+    }
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / g.N), n = (int)(i % g.N);
     float v = 0.f;
@@ -238,11 +278,11 @@ __global__ void __launch_bounds__(256) tc2_splitk_reduce_kernel(TcArgs g) {
   }
 }
 
-template <bool AMN, bool BMN>
+template <bool AMN, bool BMN, bool ASUM>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcArgs& g, int grid,
                cudaStream_t st) {
   constexpr size_t smem = (size_t)kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 8 * kStgBytes + 512;
-  auto kern = svla_gemm_tc2_kernel<AMN, BMN>;
+  auto kern = svla_gemm_tc2_kernel<AMN, BMN, ASUM>;
   static bool attr_set = false;
   if (!attr_set) {
     SVLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -273,7 +313,7 @@ int svla_gemm_tc2(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   const int tiles = tiles_m2 * g.tiles_n;
   if (tiles * 2 <= clusters && kb_total >= 32) {
     splits = std::min({clusters / tiles, kb_total / 8, 32});
-    const size_t per = (size_t)d->M * d->N * sizeof(float);
+    const size_t per = (size_t)d->M * ((size_t)d->N + 1) * sizeof(float);
     splits = (int)std::min<size_t>((size_t)splits, ctx->ws_bytes / std::max<size_t>(per, 1));
     splits = std::max(splits, 1);
   }
@@ -285,6 +325,8 @@ int svla_gemm_tc2(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   g.aux = d->aux; g.ldaux = d->ldaux; g.dtypeAux = d->dtypeAux;
   g.epilogue = d->epilogue; g.accumulate = d->accumulate; g.alpha = d->alpha;
   g.ws = reinterpret_cast<float*>(ctx->ws);
+  g.asum = (amn && bmn) ? d->colsum_a : nullptr;
+  g.asum_ws = g.ws + (size_t)g.splits * d->M * d->N;
   static const int dbg_env = getenv("SVLA_TC_DBG") ? atoi(getenv("SVLA_TC_DBG")) : 0;
   g.dbg = dbg_env;
 
@@ -304,9 +346,10 @@ int svla_gemm_tc2(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
     g.tma_store = 1;
   }
   const int grid = 2 * std::min(tiles * g.splits, clusters);
-  if (!amn && !bmn) rc = launch_tc2<false, false>(ma, mb, mc, g, grid, st);
-  else if (!amn && bmn) rc = launch_tc2<false, true>(ma, mb, mc, g, grid, st);
-  else rc = launch_tc2<true, true>(ma, mb, mc, g, grid, st);
+  if (!amn && !bmn) rc = launch_tc2<false, false, false>(ma, mb, mc, g, grid, st);
+  else if (!amn && bmn) rc = launch_tc2<false, true, false>(ma, mb, mc, g, grid, st);
+  else if (g.asum) rc = launch_tc2<true, true, true>(ma, mb, mc, g, grid, st);
+  else rc = launch_tc2<true, true, false>(ma, mb, mc, g, grid, st);
   if (rc) return rc;
   if (g.splits > 1) {
     const long long total = (long long)d->M * d->N;

@@ -105,6 +105,8 @@ struct TcArgs {
   int epilogue, accumulate;
   float alpha;
   float* ws;
+  float* asum;     // bias gradient fused into a weight-gradient launch (gemm_tc2.cu), or NULL
+  float* asum_ws;  // its split-K partials
   int tma_store;
   int dbg;  // SVLA_TC_DBG experiments: 1 = skip the epilogue entirely, 2 = TMEM loads only (no global stores)
 };

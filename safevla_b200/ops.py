@@ -115,7 +115,7 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 # ---- dense path --------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, trans_b=True, bias=None,
          residual=None, aux=None, epilogue=L.EPI_NONE, accumulate=False, alpha=1.0, impl=0,
-         M=None, N=None, K=None, lda=None, ldb=None, ldc=None):
+         M=None, N=None, K=None, lda=None, ldb=None, ldc=None, colsum_a=None):
     """out[M,N] = epi(alpha * op(a) op(b) + bias) [+ residual].  a/b/out are 2-D views whose last
     dim is contiguous (row stride = leading dimension).  trans_b=True is the nn.Linear layout."""
     for t in (a, b, out, residual, aux):
@@ -147,6 +147,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     if aux is not None:
         d.aux, d.ldaux, d.dtypeAux = ptr(aux), aux.stride(0), dt(aux)
     d.epilogue, d.accumulate, d.alpha, d.impl = epilogue, int(accumulate), alpha, impl
+    if colsum_a is not None:  # bias gradient of the same linear, accumulated (trans_a launches only)
+        assert trans_a and colsum_a.dtype == torch.float32 and colsum_a.numel() >= M
+        d.colsum_a = ptr(colsum_a)
     if PROFILE is None:
         check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
         return out

@@ -89,9 +89,8 @@ class Tower:
         gw = self.W.g(wname, wshape, count)
         if gw.dim() != 2:
             gw = gw.view(gw.shape[0], -1)
-        ops.gemm(dy, x, gw, trans_a=True, trans_b=False, accumulate=True)
-        if bname:
-            ops.colsum(dy, self.W.g(bname, None, count).reshape(-1), accumulate=True)
+        gb = self.W.g(bname, None, count).reshape(-1) if bname else None
+        ops.gemm(dy, x, gw, trans_a=True, trans_b=False, accumulate=True, colsum_a=gb)  # dW and db in one launch
         if dx is not None:
             w = self.W.w(wname, wshape, count, dtype=dy.dtype)
             if w.dim() != 2:
@@ -229,12 +228,10 @@ class Tower:
                                  t[f"lse_{l}"], Rc, S, scale=1.0 / math.sqrt(DH))
                 xc = x.view(Rc, S * D)[:, :D]
                 # K/V projections of every token
-                ops.gemm(dkv, x, gwi[D:3 * D], trans_a=True, trans_b=False, accumulate=True)
-                ops.colsum(dkv, gbi[D:3 * D], accumulate=True)
+                ops.gemm(dkv, x, gwi[D:3 * D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[D:3 * D])
                 dxn = ops.gemm(dkv, wi[D:3 * D], self._new(Ms, D), trans_b=False)
                 # Q projection + residual of the CLS row
-                ops.gemm(dq0, xc, gwi[0:D], trans_a=True, trans_b=False, accumulate=True)
-                ops.colsum(dq0, gbi[0:D], accumulate=True)
+                ops.gemm(dq0, xc, gwi[0:D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[0:D])
                 dxc = ops.gemm(dq0, wi[0:D], self._new(Rc, D), trans_b=False, residual=ds1)
                 ops.copy_rows(dxc, dxn, Rc, D, dmap=RowMap(1, S, 0), accumulate=True)
                 dx = dxn

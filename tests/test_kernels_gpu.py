@@ -443,6 +443,27 @@ def test_gemm_tcgen05(dev, M, N, K, ta, tb):
     assert (acc.double() - exp2).abs().max().item() < 2e-5 * max(scale, 1.0) * max(1.0, (K / 512) ** 0.5)
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 117 * 256), (2048, 512, 117 * 64), (1536, 512, 4000), (256, 256, 64),
+                                   (512, 384, 84 * 96), (300, 512, 1000), (128, 512, 2048), (20, 512, 8192)])
+def test_gemm_wgrad_fused_bias_gradient(dev, M, N, K):
+    """dW = dY^T X with the bias gradient colsum(dY) out of the same launch (ones-MMA in the pair kernel; the
+    dispatcher runs a separate column-sum pass for shapes that kernel does not take)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    dy = (torch.randn(K, M, generator=g) * 0.5).to(dev, torch.bfloat16)
+    x = (torch.randn(K, N, generator=g) * 0.5).to(dev, torch.bfloat16)
+    gw0, gb0 = torch.randn(M, N, generator=g).to(dev), torch.randn(M, generator=g).to(dev)
+    gw, gb = gw0.clone(), gb0.clone()
+    _ops().gemm(dy, x, gw, trans_a=True, trans_b=False, accumulate=True, colsum_a=gb)
+    ref_w = gw0.double() + dy.double().t() @ x.double()
+    ref_b = gb0.double() + dy.double().sum(0)
+    assert (gw.double() - ref_w).abs().max().item() < 2e-5 * ref_w.abs().max().item() * max(1.0, (K / 512) ** 0.5)
+    assert (gb.double() - ref_b).abs().max().item() < 2e-5 * max(ref_b.abs().max().item(), 1.0) * max(1.0, (K / 512) ** 0.5)
+    # bit-stable run to run
+    gw2, gb2 = gw0.clone(), gb0.clone()
+    _ops().gemm(dy, x, gw2, trans_a=True, trans_b=False, accumulate=True, colsum_a=gb2)
+    assert torch.equal(gw, gw2) and torch.equal(gb, gb2)
+
+
 @pytest.mark.parametrize("mode,S,B", [(0, 117, 5), (0, 128, 2), (1, 128, 3), (1, 16, 1), (0, 33, 300)])
 def test_attention_tcgen05_vs_cuda_core(dev, mode, S, B):
     """tcgen05 attention (forced) against the CUDA-core kernel on identical bf16 inputs, fwd and bwd."""
