@@ -151,6 +151,192 @@ __global__ void __launch_bounds__(128) attn_cls_bwd_kernel(const T* __restrict__
   dqb[lane + 32] = from_f<T>(q1 * scale);
 }
 
+
+// ---- bf16 fast path ------------------------------------------------------------------------------------------
+// A warp still owns one (sequence, head), but a K / V row (64 bf16 = 128 B) is read by EIGHT lanes with one 16-byte
+// load each, so a warp instruction covers four whole rows (four full 128-byte lines) instead of 32 partial ones.
+// lane = (r, c): r = lane / 8 picks the row of the quad, c = lane % 8 the 8-column slice.  Dot products reduce over
+// the 8 lanes of a row group (3 shuffles); the weighted sums reduce over the 4 row groups at the very end.
+constexpr int kQuads = 64;  // S <= 256
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(h[e]);
+    f[2 * e] = t.x; f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ float rows4_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+template <int NQ>  // key quads: S <= 4 * NQ
+__global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
+                                                                const __nv_bfloat16* __restrict__ k,
+                                                                const __nv_bfloat16* __restrict__ v, long long ldkv,
+                                                                __nv_bfloat16* __restrict__ o, long long ldo,
+                                                                float* __restrict__ lse, int B, int S, int H, float scale) {
+  const int lane = threadIdx.x & 31, r = lane >> 3, c = lane & 7;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)B * H) return;
+  const int b = (int)(wid / H), h = (int)(wid % H);
+  float qv[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(q + (long long)b * ldq + h * DH + c * 8)), qv);
+  const __nv_bfloat16* kb = k + (long long)b * S * ldkv + h * DH + c * 8;
+  const __nv_bfloat16* vb = v + (long long)b * S * ldkv + h * DH + c * 8;
+  constexpr int kBatch = 8;  // quads with loads in flight together
+  float sc[NQ];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i0 = 0; i0 < NQ; i0 += kBatch) {
+    uint4 kr[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int j = 4 * (i0 + i) + r;
+      if (j < S) kr[i] = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j * ldkv));
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int j = 4 * (i0 + i) + r;
+      float kf[8], acc = 0.f;
+      if (j < S) {
+        unpack8(kr[i], kf);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc = fmaf(qv[d], kf[d], acc);
+      }
+      acc = group8_sum(acc) * scale;
+      sc[i0 + i] = (j < S) ? acc : -INFINITY;
+      mx = fmaxf(mx, sc[i0 + i]);
+    }
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  float sum = 0.f, acc[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+#pragma unroll
+  for (int i0 = 0; i0 < NQ; i0 += kBatch) {
+    uint4 vr[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int j = 4 * (i0 + i) + r;
+      if (j < S) vr[i] = __ldg(reinterpret_cast<const uint4*>(vb + (long long)j * ldkv));
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int j = 4 * (i0 + i) + r;
+      if (j < S) {
+        const float p = __expf(sc[i0 + i] - mx);
+        sum += p;
+        float vf[8];
+        unpack8(vr[i], vf);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[d] = fmaf(p, vf[d], acc[d]);
+      }
+    }
+  }
+  sum = rows4_sum(sum);  // every lane of a row group holds the same p, so this is the full row sum
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) acc[d] = rows4_sum(acc[d]) * inv;
+  if (r == 0) *reinterpret_cast<uint4*>(o + (long long)b * ldo + h * DH + c * 8) = pack8(acc);
+  if (lane == 0) lse[wid] = mx + __logf(sum);
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(128, 4) attn_cls_bwd_bf16_kernel(
+    const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k,
+    const __nv_bfloat16* __restrict__ v, long long ldkv, const __nv_bfloat16* __restrict__ o,
+    const __nv_bfloat16* __restrict__ d_o, long long ldo, __nv_bfloat16* __restrict__ dq, long long lddq,
+    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long lddkv, const float* __restrict__ lse, int B,
+    int S, int H, float scale) {
+  const int lane = threadIdx.x & 31, r = lane >> 3, c = lane & 7;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)B * H) return;
+  const int b = (int)(wid / H), h = (int)(wid % H);
+  float qv[8], dov[8], ov[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(q + (long long)b * ldq + h * DH + c * 8)), qv);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(d_o + (long long)b * ldo + h * DH + c * 8)), dov);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(o + (long long)b * ldo + h * DH + c * 8)), ov);
+  float delta = 0.f;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) delta = fmaf(ov[d], dov[d], delta);
+  delta = group8_sum(delta);
+  const float l_ = lse[wid];
+  const __nv_bfloat16* kb = k + (long long)b * S * ldkv + h * DH + c * 8;
+  const __nv_bfloat16* vb = v + (long long)b * S * ldkv + h * DH + c * 8;
+  __nv_bfloat16* dkb = dk + (long long)b * S * lddkv + h * DH + c * 8;
+  __nv_bfloat16* dvb = dv + (long long)b * S * lddkv + h * DH + c * 8;
+  float dqa[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) dqa[d] = 0.f;
+  constexpr int kBatch = 8;  // quads with loads in flight together
+#pragma unroll 1
+  for (int i0 = 0; i0 < NQ; i0 += kBatch) {
+    if (4 * i0 >= S) break;
+    uint4 kr[kBatch], vr[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int j = 4 * (i0 + i) + r;
+      if (j < S) {
+        kr[i] = __ldg(reinterpret_cast<const uint4*>(kb + (long long)j * ldkv));
+        vr[i] = __ldg(reinterpret_cast<const uint4*>(vb + (long long)j * ldkv));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int j = 4 * (i0 + i) + r;
+      const bool ok = j < S;
+      float kf[8], vf[8], s = 0.f, dp = 0.f;
+      if (ok) {
+        unpack8(kr[i], kf);
+        unpack8(vr[i], vf);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          s = fmaf(qv[d], kf[d], s);
+          dp = fmaf(dov[d], vf[d], dp);
+        }
+      }
+      s = group8_sum(s);
+      dp = group8_sum(dp);
+      if (ok) {
+        const float p = __expf(s * scale - l_);
+        const float dsj = p * (dp - delta);
+        float a[8], bb[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          a[d] = scale * dsj * qv[d];
+          bb[d] = p * dov[d];
+          dqa[d] = fmaf(dsj, kf[d], dqa[d]);
+        }
+        *reinterpret_cast<uint4*>(dkb + (long long)j * lddkv) = pack8(a);
+        *reinterpret_cast<uint4*>(dvb + (long long)j * lddkv) = pack8(bb);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 8; ++d) dqa[d] = rows4_sum(dqa[d]) * scale;
+  if (r == 0) *reinterpret_cast<uint4*>(dq + (long long)b * lddq + h * DH + c * 8) = pack8(dqa);
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
 
 extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, const void* k, const void* v,
@@ -161,6 +347,20 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
   SVLA_CHECK_ARG(ldq % 4 == 0 && ldkv % 4 == 0 && ldo % 4 == 0, "leading dims must be multiples of 4");
   if (B <= 0) return SVLA_OK;
   const long long threads = (long long)B * H * 32;
+  if (dtype == SVLA_BF16 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) && al16(v) && al16(o)) {
+    const unsigned grid = (unsigned)((threads + 127) / 128);
+    const auto st = as_stream(stream);
+#define SVLA_CLS_FWD(NQ_)                                                                                          \
+  attn_cls_fwd_bf16_kernel<NQ_><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,         \
+                                                      (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, lse, B, S, \
+                                                      H, scale)
+    if (S <= 64) SVLA_CLS_FWD(16);
+    else if (S <= 128) SVLA_CLS_FWD(32);
+    else SVLA_CLS_FWD(64);
+#undef SVLA_CLS_FWD
+    SVLA_LAUNCH_CHECK();
+    return SVLA_OK;
+  }
   SVLA_DISPATCH_DTYPE(dtype, T, (attn_cls_fwd_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
                                     (const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (T*)o, ldo, lse, B, S, H, scale)));
   SVLA_LAUNCH_CHECK();
@@ -175,6 +375,15 @@ extern "C" int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, co
   SVLA_CHECK_ARG(dh == DH && S >= 1 && S <= 32 * kMaxChunks, "head dim must be 64 and S <= 256");
   if (B <= 0) return SVLA_OK;
   const long long threads = (long long)B * H * 32;
+  if (dtype == SVLA_BF16 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 && lddkv % 8 == 0 && al16(q) &&
+      al16(k) && al16(v) && al16(o) && al16(d_o) && al16(dq) && al16(dk) && al16(dv)) {
+    attn_cls_bwd_bf16_kernel<64><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (const __nv_bfloat16*)o,
+        (const __nv_bfloat16*)d_o, ldo, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, lddkv, lse, B, S,
+        H, scale);
+    SVLA_LAUNCH_CHECK();
+    return SVLA_OK;
+  }
   SVLA_DISPATCH_DTYPE(dtype, T, (attn_cls_bwd_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
                                     (const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)o, (const T*)d_o, ldo,
                                     (T*)dq, lddq, (T*)dk, (T*)dv, lddkv, lse, B, S, H, scale)));
