@@ -259,6 +259,14 @@ int svla_attn_tc_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
 int svla_attn_tc_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
                      const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
                      const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st);
+// attn_tc2.cu: 128 < S <= 256
+bool svla_attn_tc2_supported(int mode, int dtype, int S, int dh, long long ld, long long ldo, const void* q,
+                             const void* k, const void* v, const void* o);
+int svla_attn_tc2_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                      long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st);
+int svla_attn_tc2_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
+                      const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
+                      const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st);
 static int g_attn_impl = 0;  // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel (error when unsupported)
 extern "C" int svla_set_attn_impl(int impl) {
   g_attn_impl = impl;
@@ -275,6 +283,9 @@ extern "C" int svla_attn_fwd(svla_ctx* ctx, int mode, const void* q, const void*
   SVLA_CHECK_ARG(ld % 4 == 0 && ldo % 4 == 0, "leading dims must be multiples of 4");
   if (B <= 0) return SVLA_OK;
   {
+    const bool tc2_ok = svla_attn_tc2_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o);
+    if (tc2_ok && g_attn_impl != 1)
+      return svla_attn_tc2_fwd(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, as_stream(stream));
     const bool tc_ok = svla_attn_tc_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o);
     if (g_attn_impl == 2 && !tc_ok) {
       svla_set_error("svla_attn_fwd: tcgen05 attention requested for an unsupported case (S=%d dtype=%d mode=%d)", S,
@@ -308,9 +319,12 @@ extern "C" int svla_attn_bwd(svla_ctx* ctx, int mode, const void* q, const void*
   SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
   if (B <= 0) return SVLA_OK;
   {
-    const bool tc_ok = svla_attn_tc_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o) && ldd % 8 == 0 &&
-                       ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
-                         reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(d_o)) & 15) == 0;
+    const bool grads_ok = ldd % 8 == 0 && ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+                                            reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(d_o)) & 15) == 0;
+    if (grads_ok && g_attn_impl != 1 && svla_attn_tc2_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o))
+      return svla_attn_tc2_bwd(ctx, mode, q, k, v, ld, o, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale,
+                               as_stream(stream));
+    const bool tc_ok = svla_attn_tc_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o) && grads_ok;
     if (g_attn_impl == 2 && !tc_ok) {
       svla_set_error("svla_attn_bwd: tcgen05 attention requested for an unsupported case (S=%d dtype=%d mode=%d)", S,
                      dtype, mode);

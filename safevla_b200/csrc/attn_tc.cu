@@ -19,130 +19,9 @@
 int svla_make_tmap_bf16(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
                         CUtensorMap* out);  // gemm_tc.cu
 
+#include "attn_tc_common.cuh"
+
 namespace {
-
-constexpr int DH = 64, TS = 128;  // tile: 128 queries x 128 keys
-constexpr float kLog2e = 1.4426950408889634f;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: D=f32, A=B=bf16
-__host__ __device__ constexpr uint32_t idesc(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// [128 rows x 64] bf16 operand tile as TMA lands it (row = 128 B, 128B swizzle):
-//   K-major view  (rows = M/N, 64 = K): k-step kk (16 elements) -> +32 B
-//   MN-major view (rows = K, 64 = M/N): k-step kk (16 rows)     -> +2048 B
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int kk) { return umma_desc(base + kk * 32, 16, 1024); }
-__device__ __forceinline__ uint64_t desc_mnmajor64(uint32_t base, int kk) { return umma_desc(base + kk * 2048, 8192, 1024); }
-// [128 rows x 128] bf16 P / dS tile written by the threads as two 64-column chunks of [128 rows x 128 B]:
-//   K-major view  (rows = M queries, 128 = K keys): k-step kk -> chunk kk/4, +32 B * (kk%4)
-//   MN-major view (rows = K queries, 128 = M keys, two 64-chunks 16384 B apart): k-step kk -> +2048 B
-__device__ __forceinline__ uint64_t desc_p_kmajor(uint32_t base, int kk) {
-  return umma_desc(base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-}
-__device__ __forceinline__ uint64_t desc_p_mnmajor(uint32_t base, int kk) { return umma_desc(base + kk * 2048, 16384, 1024); }
-
-// write 8 consecutive bf16 (columns c8*8 .. +8 of row i) of a P / dS tile
-__device__ __forceinline__ void store_p8(uint8_t* base, int i, int c8, const float* v) {
-  uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-  const int chunk = c8 >> 3, cc = c8 & 7;
-  *reinterpret_cast<uint4*>(base + chunk * 16384 + i * 128 + ((cc ^ (i & 7)) << 4)) = u;
-}
-
-struct AttnTcArgs {
-  int mode, B, S, H;
-  float scale;
-  const int64_t* traj;
-  float* lse;
-  __nv_bfloat16* o; long long ldo;
-  const __nv_bfloat16* o_in; const __nv_bfloat16* d_o;
-  __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long ldd;
-};
-
-__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const uint32_t* r = half ? r1 : r0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 u;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        h[e] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]) * mul, __uint_as_float(r[j + 2 * e + 1]) * mul);
-      *reinterpret_cast<uint4*>(dst + half * 32 + j) = u;
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------ forward
 // Shared memory per CTA: Q | K | V (3 x 16 KB); once S = Q K^T has retired, Q|K are dead and P (32 KB) is written

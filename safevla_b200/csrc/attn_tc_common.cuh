@@ -1,0 +1,67 @@
+// Helpers shared by the tcgen05 attention kernels (attn_tc.cu: S <= 128, attn_tc2.cu: 128 < S <= 256).
+#pragma once
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int DH = 64, TS = 128;  // tile: 128 queries x 128 keys
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// instruction descriptor: D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// [128 rows x 64] bf16 operand tile as TMA lands it (row = 128 B, 128B swizzle):
+//   K-major view  (rows = M/N, 64 = K): k-step kk (16 elements) -> +32 B
+//   MN-major view (rows = K, 64 = M/N): k-step kk (16 rows)     -> +2048 B
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int kk) { return umma_desc(base + kk * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mnmajor64(uint32_t base, int kk) { return umma_desc(base + kk * 2048, 8192, 1024); }
+// [128 rows x 128] bf16 P / dS tile written by the threads as two 64-column chunks of [128 rows x 128 B]:
+//   K-major view  (rows = M queries, 128 = K keys): k-step kk -> chunk kk/4, +32 B * (kk%4)
+//   MN-major view (rows = K queries, 128 = M keys, two 64-chunks 16384 B apart): k-step kk -> +2048 B
+__device__ __forceinline__ uint64_t desc_p_kmajor(uint32_t base, int kk) {
+  return umma_desc(base + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_p_mnmajor(uint32_t base, int kk) { return umma_desc(base + kk * 2048, 16384, 1024); }
+
+// write 8 consecutive bf16 (columns c8*8 .. +8 of row i) of a P / dS tile
+__device__ __forceinline__ void store_p8(uint8_t* base, int i, int c8, const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  const int chunk = c8 >> 3, cc = c8 & 7;
+  *reinterpret_cast<uint4*>(base + chunk * 16384 + i * 128 + ((cc ^ (i & 7)) << 4)) = u;
+}
+
+struct AttnTcArgs {
+  int mode, B, S, H;
+  float scale;
+  const int64_t* traj;
+  float* lse;
+  __nv_bfloat16* o; long long ldo;
+  const __nv_bfloat16* o_in; const __nv_bfloat16* d_o;
+  __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long ldd;
+};
+
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t* r = half ? r1 : r0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h[e] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]) * mul, __uint_as_float(r[j + 2 * e + 1]) * mul);
+      *reinterpret_cast<uint4*>(dst + half * 32 + j) = u;
+    }
+  }
+}
+
+}  // namespace

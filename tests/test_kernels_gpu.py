@@ -470,7 +470,8 @@ def test_gemm_wgrad_fused_bias_gradient(dev, M, N, K):
     assert torch.equal(gw, gw2) and torch.equal(gb, gb2)
 
 
-@pytest.mark.parametrize("mode,S,B", [(0, 117, 5), (0, 128, 2), (1, 128, 3), (1, 16, 1), (0, 33, 300)])
+@pytest.mark.parametrize("mode,S,B", [(0, 117, 5), (0, 128, 2), (1, 128, 3), (1, 16, 1), (0, 33, 300), (0, 201, 7),
+                                      (0, 256, 3), (1, 256, 2), (0, 129, 160), (1, 200, 5)])
 def test_attention_tcgen05_vs_cuda_core(dev, mode, S, B):
     """tcgen05 attention (forced) against the CUDA-core kernel on identical bf16 inputs, fwd and bwd."""
     H, D = 8, 512
