@@ -160,7 +160,7 @@ def scan_roofline(dev, pk):
     dl, dv = torch.empty_like(logits), torch.empty(T * N, device=dev)
     scal = torch.empty(16, device=dev)
 
-    def t_of(fn, n=10):
+    def t_of(fn, n=20):
         for _ in range(3):
             fn()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
@@ -208,6 +208,9 @@ def run_b200(args, wl, name):
     n_local = wl["N"] // world
     pk = peaks()
 
+    # GAE / fused-loss roofline shapes first: each kernel timed alone (burst conditions, like the copy that
+    # MEASURED_PEAKS.json's HBM figure comes from), not after seconds of power-capped tensor-core work
+    scan = scan_roofline(dev, pk) if world == 1 else None
     model = B200SafeActorCritic(A, C, precision=args.precision, seed=0, device=dev, chunk_rows=args.chunk_rows,
                                 extras="off", verify_dedupe=False)
     cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS)
@@ -322,7 +325,7 @@ def run_b200(args, wl, name):
                                     "note": "SURVEY 8a FLOP model x samples/s over all GPUs; includes every non-GEMM kernel"},
     }
     if world == 1:
-        line["roofline_scan"] = scan_roofline(dev, pk)
+        line["roofline_scan"] = scan
         if not args.no_cpu_baseline:
             v, t, desc = cpu_sample(wl, 1, 0, sample_T=min(T, 32), sample_N=1)
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -219,6 +219,14 @@ int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, const void* k
                       long long lddkv, int dtype, const float* lse, int B, int S, int H, int dh, float scale,
                       svla_stream stream);
 
+/* Single-step decoder attention against the KV cache (rollout-side T = 1 inference; llama/model.py:224-247,279-317,
+ * episode-start mask allenact_dino_transformer.py:386-397).  q [N, H*dh] (ldq); cache_k / cache_v [N, cache_rows,
+ * H*dh] (row stride ldc) already holding this step's K / V at row `pos`; sampler n attends to rows
+ * [max(pos - time_step[n], 0), pos] (time_step NULL: only row pos); o [N, H*dh]. */
+int svla_attn_decode(svla_ctx* ctx, const void* q, long long ldq, const void* cache_k, const void* cache_v,
+                     long long cache_rows, long long ldc, const int64_t* time_step, int pos, void* o, long long ldo,
+                     int dtype, int N, int H, int dh, float scale, svla_stream stream);
+
 /* SwiGLU gate (llama/model.py:360): g = silu(a) * b, a|b packed as [rows, 2*F] (w1 | w3 outputs). */
 int svla_swiglu_fwd(svla_ctx* ctx, const void* ab, void* g, int dtype, long long rows, int F, svla_stream stream);
 int svla_swiglu_bwd(svla_ctx* ctx, const void* ab, const void* dg, void* dab, int dtype, long long rows, int F,

@@ -87,6 +87,8 @@ PROTOTYPES: Dict[str, list] = {
                           C.c_float, c_p],
     "svla_attn_cls_bwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, C.c_int, c_p,
                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
+    "svla_attn_decode": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_ll, c_p, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.c_int,
+                         C.c_int, C.c_float, c_p],
     "svla_swiglu_fwd": [c_p, c_p, c_p, C.c_int, c_ll, C.c_int, c_p],
     "svla_swiglu_bwd": [c_p, c_p, c_p, c_p, C.c_int, c_ll, C.c_int, c_p],
     "svla_embed_time_fwd": [c_p, c_p, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,

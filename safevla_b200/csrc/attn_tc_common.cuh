@@ -64,4 +64,26 @@ __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* 
   }
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// 32 consecutive fp32 accumulator columns -> 32 bf16 (64 B) of one output row
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t* r, float mul) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      h[e] = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]) * mul, __uint_as_float(r[j + 2 * e + 1]) * mul);
+    *reinterpret_cast<uint4*>(dst + j) = u;
+  }
+}
+
 }  // namespace

@@ -92,7 +92,7 @@ class B200SafeActorCritic(nn.Module):
                  goal_sensor_uuid: str = "natural_language_spec", rgb_uuid: str = "rgb_dinov2",
                  manip_uuid: str = "manipulation_rgb_dinov2", in_hand_uuid: str = "an_object_is_in_hand",
                  time_step_uuid: str = "time_step", traj_idx_uuid: str = "traj_index", extras: str = "eager",
-                 verify_dedupe: bool = True):
+                 verify_dedupe: bool = True, max_steps: int = 1000):
         super().__init__()
         assert precision in ("bf16", "fp32")
         if not torch.cuda.is_available():
@@ -129,7 +129,11 @@ class B200SafeActorCritic(nn.Module):
         self._anchor = torch.zeros(1, device=self.dev, requires_grad=True)
         self._ctx_cache: Optional[RolloutContext] = None
         self._tok_cache: Dict[bytes, Tuple[torch.Tensor, torch.Tensor]] = {}
+        # rollout-side (T = 1) state: position in the KV caches (allenact_dino_transformer.py:376-406) and the
+        # per-tower, per-layer caches [N, max_steps, 512] (llama/model.py:224-247), allocated on the first step
+        self.max_steps = max_steps
         self.time_step_counter = 0
+        self._kv: Optional[List[List[Tuple[torch.Tensor, torch.Tensor]]]] = None
         self.train()
 
     # ------------------------------------------------------------------ naming / state dict
@@ -195,7 +199,22 @@ class B200SafeActorCritic(nn.Module):
         return None
 
     def sampler_select(self, keep: list):
-        return None  # update path holds no per-sampler cache (KV cache belongs to the T=1 rollout path)
+        """Keeps the KV-cache rows of the surviving samplers (llama/model.py:238-244; called by the engine when
+        task samplers finish, allenact_dino_transformer.py:197-199)."""
+        if self._kv is None:
+            return
+        for tw in self._kv:
+            for l, (k, v) in enumerate(tw):
+                if k.shape[0] == 1 and len(keep) > 1:
+                    tw[l] = (k.repeat(len(keep), 1, 1) * 0, v.repeat(len(keep), 1, 1) * 0)
+                else:
+                    tw[l] = (k[keep].contiguous(), v[keep].contiguous())
+
+    def _step_caches(self, N: int):
+        if self._kv is None or self._kv[0][0][0].shape[0] != N:
+            mk = lambda: torch.zeros(N, self.max_steps, D, device=self.dev, dtype=self.adt)  # noqa: E731
+            self._kv = [[(mk(), mk()) for _ in range(3)] for _ in TOWERS]
+        return self._kv
 
     # ------------------------------------------------------------------ observation-side preparation
     def _decode_rows(self, rows_u8: np.ndarray) -> List[str]:
@@ -209,6 +228,8 @@ class B200SafeActorCritic(nn.Module):
             return self._ctx_cache
         R = T * N
         dev = self.dev
+        if T > 1:  # an update-mode forward restarts the rollout-side cache position (:376-377)
+            self.time_step_counter = 0
 
         def tokens(x):
             x = x.to(dev, non_blocking=True).reshape(R, 384, TOK).contiguous()
@@ -315,9 +336,7 @@ class B200SafeActorCritic(nn.Module):
                 masks: torch.Tensor):
         T, N = prev_actions.shape
         if T == 1:
-            raise NotImplementedError(
-                "single-step (KV-cache) rollout inference is outside the update path built this round "
-                "(SURVEY.md section 8f-2); run the update-mode forward with T > 1")
+            return self._forward_step(observations, memory, prev_actions, masks)
         rc = self.prepare({k: v[:T] for k, v in observations.items()}, T, N)
         pa = prev_actions.to(self.dev).contiguous()
         mk = masks.to(self.dev, dtype=torch.float32).reshape(T, N).contiguous()
@@ -334,6 +353,35 @@ class B200SafeActorCritic(nn.Module):
         extras = self._extras(outs[COST])
         aco = SafeActorCriticOutput(distributions=CategoricalDistr(logits=outs[ACTOR]), values=outs[CRITIC],
                                     c_values=outs[COST], extras=extras)
+        return aco, memory
+
+    @torch.no_grad()
+    def _forward_step(self, observations, memory, prev_actions, masks):
+        """Rollout-side single step (T = 1): encoder on the N current observations, KV-cache decoder step
+        (allenact_dino_transformer.py:376-406).  No autograd graph: the engine collects under no_grad."""
+        N = prev_actions.shape[1]
+        if self.time_step_counter >= self.max_steps:
+            self.time_step_counter = 0
+        pos = self.time_step_counter
+        self._ctx_cache = None  # rollout observations are fresh every step: never reuse a cached context
+        rc = self.prepare({k: v[:1] for k, v in observations.items()}, 1, N)
+        pa = prev_actions.to(self.dev).reshape(1, N).contiguous()
+        mk = masks.to(self.dev, dtype=torch.float32).reshape(1, N).contiguous()
+        kv = self._step_caches(N)
+        outs = {}
+        for idx in (ACTOR, CRITIC, COST):
+            tw = self.towers[idx]
+            obs_embed = torch.empty(N, D, device=self.dev, dtype=self.adt)
+            for (r0, r1) in self._chunks(N):
+                vis, th = self._chunk_inputs(rc, r0, r1)
+                cls, _ = tw.encoder_fwd(vis, th, rc.L, keep=False)
+                obs_embed[r0:r1].copy_(cls)
+            o = tw.decoder_step(obs_embed, pa, mk, rc.in_hand, rc.time_step, kv[idx], pos, N,
+                                want_logits=(idx == ACTOR), want_values=(idx != ACTOR))
+            outs[idx] = o["logits"] if idx == ACTOR else o["values"]
+        self.time_step_counter += 1
+        aco = SafeActorCriticOutput(distributions=CategoricalDistr(logits=outs[ACTOR]), values=outs[CRITIC],
+                                    c_values=outs[COST], extras=self._extras(outs[COST]))
         return aco, memory
 
     def _extras(self, c_values: torch.Tensor):

@@ -245,6 +245,17 @@ def attn_cls_bwd(q0, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.12
                                    ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_bwd")
 
 
+def attn_decode(q, cache_k, cache_v, time_step, pos, o, H=8, dh=64, scale=0.125):
+    """q [N, H*dh]; cache_k / cache_v [N, rows, H*dh] holding this step's K / V at row `pos`; time_step int64 [N]."""
+    N = q.shape[0]
+    assert cache_k.dim() == 3 and cache_k.stride() == cache_v.stride() and cache_k.stride(2) == 1
+    assert cache_k.stride(0) == cache_k.shape[1] * cache_k.stride(1)
+    check(_lib().svla_attn_decode(get_ctx(), ptr(q), q.stride(0), ptr(cache_k), ptr(cache_v), cache_k.shape[1],
+                                  cache_k.stride(1), ptr(time_step), int(pos), ptr(o), o.stride(0), dt(q), N, H, dh,
+                                  scale, stream_ptr()), "svla_attn_decode")
+    return o
+
+
 def swiglu_fwd(ab, g):
     F = g.shape[-1]
     check(_lib().svla_swiglu_fwd(get_ctx(), ptr(ab), ptr(g), dt(ab), g.numel() // F, F, stream_ptr()), "svla_swiglu_fwd")

@@ -320,6 +320,45 @@ class Tower:
             t.update({"hf": h, "rf": rf, "yf": yf, "b_tn": b_tn})
         return out, t
 
+    def decoder_step(self, obs_embed, prev_actions, masks, in_hand, time_step, cache, pos: int, N: int,
+                     want_logits: bool, want_values: bool):
+        """One rollout step (T = 1) of the KV-cache decoder (llama/model.py:224-247,279-317 driven by
+        allenact_dino_transformer.py:376-406): this step's K / V rows go to row `pos` of the per-layer caches
+        `cache[l] = (k, v)`, each [N, max_steps, 512] in the activation dtype, and sampler n attends to rows
+        [max(pos - time_step[n], 0), pos] -- the episode-start mask of :386-397.  obs_embed [N, 512];
+        prev_actions / time_step int64 [1, N]; masks fp32 [1, N].  Returns dict(logits [1,N,A], values [1,N,1])."""
+        W, f32, ddt = self.W, torch.float32, self.adt
+        x = self._new(N, D, dtype=f32)
+        ops.embed_time_fwd(obs_embed, prev_actions, masks, in_hand, time_step, W.p("last_actions_embed.weight"),
+                           W.p("object_in_hand_embed.weight") if in_hand is not None else None,
+                           self.div_term, x, 1, N, self.A)
+        h = x
+        for l in range(3):
+            p = f"decoder.layers.{l}."
+            ck, cv = cache[l]
+            y1 = ops.rmsnorm_fwd(h, W.p(p + "attention_norm.weight"), self._new(N, D, dtype=ddt), RMS_EPS)
+            qkv = ops.gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(N, 3 * D, dtype=ddt))
+            ops.copy_rows(qkv[:, D:2 * D], ck.view(-1, D), N, D, dmap=RowMap(1, ck.shape[1], pos))
+            ops.copy_rows(qkv[:, 2 * D:3 * D], cv.view(-1, D), N, D, dmap=RowMap(1, cv.shape[1], pos))
+            ao = ops.attn_decode(qkv[:, 0:D], ck, cv, time_step, pos, self._new(N, D, dtype=ddt),
+                                 scale=1.0 / math.sqrt(DH))
+            h2 = ops.gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(N, D, dtype=f32), residual=h)
+            y2 = ops.rmsnorm_fwd(h2, W.p(p + "ffn_norm.weight"), self._new(N, D, dtype=ddt), RMS_EPS)
+            ab = ops.gemm(y2, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
+                          self._new(N, 2 * DEC_FF, dtype=ddt))
+            g = ops.swiglu_fwd(ab, self._new(N, DEC_FF, dtype=ddt))
+            h = ops.gemm(g, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(N, D, dtype=f32), residual=h2)
+        yf = ops.rmsnorm_fwd(h, W.p("decoder.norm.weight"), self._new(N, D, dtype=ddt), RMS_EPS)
+        b = ops.gemm(yf, W.w("decoder.output.weight", dtype=ddt), self._new(N, D, dtype=f32))
+        out = {}
+        if want_logits:
+            out["logits"] = ops.gemm(b, W.p("actor.linear.weight"), self._new(N, self.A, dtype=f32),
+                                     bias=W.p("actor.linear.bias")).view(1, N, self.A)
+        if want_values:
+            out["values"] = ops.gemm(b, W.p("critic.fc.weight"), self._new(N, 1, dtype=f32),
+                                     bias=W.p("critic.fc.bias")).view(1, N, 1)
+        return out
+
     def decoder_bwd(self, dlogits, dvalues, t, prev_actions, masks, in_hand, traj_nt, perm_nt, T, N):
         """Returns d obs_embed [T*N, 512] (adt).  perm_nt[n*T+t] = t*N+n."""
         W, f32, ddt = self.W, torch.float32, self.adt

@@ -61,6 +61,30 @@ def test_oracle_reproduces_reference_golden(name):
     assert abs(t0.item() - gold["loss_lambda0"].item()) < 1e-5 * max(1, abs(t0.item()))
 
 
+@pytest.mark.parametrize("name", ["step_N3_A6_C1", "step_N2_A20_C2"])
+def test_oracle_step_mode_reproduces_reference_golden(name):
+    """Rollout-side T = 1 path (KV-cache decoder, episode-start mask, position wrap at max_steps, reset by an
+    update-mode forward): the restated oracle against the reference's per-step outputs."""
+    from oracle.make_golden_step import build_inputs as step_inputs, schedule
+    torch.set_num_threads(os.cpu_count() or 1)
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    case = gold["case"]
+    A, C = case["A"], case["C"]
+    sd = init_state_dict(A, C, case["wseed"], actor_gain=1.0)
+    ro, prev = step_inputs(case)
+    st = TO.StepState(case["max_steps"])
+    it = iter(gold["steps"])
+    for kind, t0, t1 in schedule(case):
+        if kind == "update":
+            st.reset_positions()
+            continue
+        rec = next(it)
+        obs = {k: v[t0:t1] for k, v in ro["observations"].items()}
+        out = TO.safe_model_step(sd, obs, prev[t0:t1], ro["masks"][t0:t1], A, C, st)
+        for k in ("logits", "values", "c_values"):
+            assert relerr(out[k], rec[k]) < 2e-5, (t0, k)
+
+
 def test_oracle_matches_reference_live():
     """Runs the unmodified reference (only where /root/reference exists, i.e. the build container)."""
     from oracle import ref_shim

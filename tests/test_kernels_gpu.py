@@ -353,6 +353,30 @@ def test_attention_cls(dev, S, dt_):
     assert relerr(dkv[:, D:].float(), vr.grad) < tol
 
 
+@pytest.mark.parametrize("dt_", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,pos,rows", [(3, 0, 8), (5, 7, 8), (64, 130, 256), (2, 499, 500)])
+def test_attention_decode_kv_cache(dev, N, pos, rows, dt_):
+    """Single-step attention against the KV cache with the episode-start mask (llama/model.py:279-317,
+    allenact_dino_transformer.py:386-397)."""
+    H, D = 8, 512
+    g = torch.Generator().manual_seed(N * 1000 + pos)
+    ck = (torch.randn(N, rows, D, generator=g) * 0.5).to(dev, dt_)
+    cv = (torch.randn(N, rows, D, generator=g) * 0.5).to(dev, dt_)
+    q = (torch.randn(N, 3 * D, generator=g) * 0.5).to(dev, dt_)[:, :D]  # strided view like the packed QKV buffer
+    ts = torch.randint(0, pos + 5, (1, N), generator=g).to(dev)
+    o = torch.empty(N, D, device=dev, dtype=dt_)
+    _ops().attn_decode(q, ck, cv, ts, pos, o)
+    start = torch.clamp(pos - ts.view(N), min=0)
+    ar = torch.arange(pos + 1, device=dev)
+    mask = (start[:, None] <= ar[None, :])[:, None, None, :]
+    qq = q.float().view(N, 1, H, 64).transpose(1, 2)
+    kk = ck[:, :pos + 1].float().view(N, pos + 1, H, 64).transpose(1, 2)
+    vv = cv[:, :pos + 1].float().view(N, pos + 1, H, 64).transpose(1, 2)
+    sc = (qq @ kk.transpose(-1, -2) * 0.125).masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(sc, -1) @ vv).transpose(1, 2).reshape(N, D)
+    assert relerr(o.float(), ref) < (2e-5 if dt_ == torch.float32 else 1e-2)
+
+
 # ------------------------------------------------------------------------------------------ glue
 def test_swiglu(dev):
     rows, F = 300, 1536

@@ -159,3 +159,71 @@ def test_updater_matches_oracle_update(dev):
             worst = (k, err)
     assert moved > 5e-4  # two Adam steps of lr 1e-3 really moved the parameters
     assert worst[1] < 2e-5, worst
+
+
+# ------------------------------------------------------------------------------------------ rollout-side T = 1
+@pytest.mark.parametrize("name", ["step_N3_A6_C1", "step_N2_A20_C2"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_single_step_inference_matches_reference(dev, name, precision):
+    """forward() with T = 1 (KV-cache decoder step, episode-start mask, position wrap, reset by an update-mode
+    forward) against the reference's per-step golden outputs; sampled actions identical given the same seed."""
+    from oracle.make_golden_step import build_inputs as step_inputs, schedule
+    from safevla_b200.model import B200SafeActorCritic
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    case = gold["case"]
+    sd = init_state_dict(case["A"], case["C"], case["wseed"], actor_gain=1.0)
+    model = B200SafeActorCritic(case["A"], case["C"], precision=precision, state_dict=sd, device=dev,
+                                max_steps=case["max_steps"], extras="off")
+    ro, prev = step_inputs(case)
+    it = iter(gold["steps"])
+    tol = 1e-4 if precision == "fp32" else 5e-2  # bf16 operands, fp32 accumulation
+    for kind, t0, t1 in schedule(case):
+        obs = {k: v[t0:t1].to(dev) for k, v in ro["observations"].items()}
+        with torch.no_grad():
+            out, _ = model(obs, None, prev[t0:t1].to(dev), ro["masks"][t0:t1].to(dev))
+        if kind == "update":
+            continue
+        rec = next(it)
+        assert out.distributions.raw_logits.shape == rec["logits"].shape
+        assert relerr(out.distributions.raw_logits, rec["logits"]) < tol, (t0, "logits")
+        for got, ref in ((out.values, rec["values"]), (out.c_values, rec["c_values"])):
+            # N scalars per step: scale the bf16 tolerance by at least 0.25 so a near-zero value is not a 0/0 test
+            scale = ref.abs().max().item() if precision == "fp32" else max(ref.abs().max().item(), 0.25)
+            assert (got.cpu().double() - ref.double()).abs().max().item() < tol * scale, (t0, got, ref)
+        if precision == "fp32":
+            # action sampling: the stock multinomial on our logits == on the reference's, same seed
+            torch.manual_seed(1234 + t0)
+            mine = out.distributions.sample().cpu()
+            torch.manual_seed(1234 + t0)
+            ref = torch.distributions.Categorical(logits=rec["logits"].to(dev)).sample().cpu()
+            assert torch.equal(mine, ref)
+            assert torch.equal(out.distributions.mode().cpu(), rec["logits"].argmax(-1))
+
+
+def test_sampler_select_keeps_cache_rows(dev):
+    from oracle.make_golden_step import build_inputs as step_inputs
+    from safevla_b200.model import B200SafeActorCritic
+    gold = torch.load(os.path.join(GOLDEN_DIR, "step_N3_A6_C1.pt"), weights_only=False)
+    case = gold["case"]
+    sd = init_state_dict(case["A"], case["C"], case["wseed"], actor_gain=1.0)
+    ro, prev = step_inputs(case)
+
+    def run(keep_after, steps):
+        model = B200SafeActorCritic(case["A"], case["C"], precision="fp32", state_dict=sd, device=dev, max_steps=16,
+                                    extras="off")
+        sel = list(range(case["N"]))
+        outs = []
+        for t in range(steps):
+            if t == keep_after:
+                sel = [0, 2]
+                model.sampler_select(sel)
+            obs = {k: v[t:t + 1, sel].to(dev) for k, v in ro["observations"].items()}
+            with torch.no_grad():
+                out, _ = model(obs, None, prev[t:t + 1, sel].to(dev), ro["masks"][t:t + 1, sel].to(dev))
+            outs.append(out.distributions.raw_logits.cpu())
+        return outs
+
+    a = run(3, 6)            # drop sampler 1 after three steps
+    b = run(10 ** 9, 6)      # never drop
+    for t in range(3, 6):
+        assert torch.allclose(a[t], b[t][:, [0, 2]], rtol=1e-5, atol=1e-6)
