@@ -201,7 +201,7 @@ def run_b200(args, wl, name):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.pop("NCCL_DEBUG", None)  # any NCCL_DEBUG level prints a version banner on stdout; keep it to the JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert wl["N"] % world == 0, "samplers must divide evenly over the ranks"
     T, A, C = wl["T"], wl["A"], wl["C"]

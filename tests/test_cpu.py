@@ -259,3 +259,36 @@ def test_library_is_sm100a_native():
     from safevla_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out[:500]
+
+
+# ------------------------------------------------------------------ checkpoint formats
+def test_checkpoint_format_conversion():
+    from safevla_b200 import checkpoint as CK
+    sd = init_state_dict(6, 1, seed=3)
+    single = {k: v for k, v in sd.items() if "critic_tsfm" not in k}
+    # 1. Lightning IL checkpoint: "model." prefix, bare-Linear actor head, plus frozen DINO weights to ignore
+    il = {"state_dict": {("model." + k).replace("actor.linear.", "actor."): v + 1.0 for k, v in single.items()
+                         if "text_encoder" not in k}}
+    il["state_dict"]["model.visual_encoder.image_encoder.model.blocks.0.attn.qkv.weight"] = torch.zeros(3)
+    il["state_dict"]["model.some_aux_head.weight"] = torch.zeros(2)
+    assert CK.detect_format(il) == "lightning"
+    conv = CK.to_model_state_dict(il)
+    assert "actor.linear.weight" in conv and "actor.weight" not in conv
+    assert torch.equal(conv["decoder.norm.weight"], sd["decoder.norm.weight"] + 1.0)
+    new, rep = CK.merge_il_checkpoint(sd, il)
+    for pre in CK.TOWER_PREFIXES:  # every tower is initialised from the IL policy
+        assert torch.equal(new[pre + "decoder.norm.weight"], sd["decoder.norm.weight"] + 1.0)
+        assert torch.equal(new[pre + "actor.linear.bias"], sd["actor.linear.bias"] + 1.0)
+    assert torch.equal(new["visual_encoder.text_encoder.shared.weight"], sd["visual_encoder.text_encoder.shared.weight"])
+    assert "some_aux_head.weight" in rep.unexpected_in_checkpoint
+    assert not any("image_encoder" in k for k in rep.unexpected_in_checkpoint)
+    assert any("text_encoder" in k for k in rep.missing_in_checkpoint) and "decoder.norm.weight" in rep.loaded
+    # 2. allenact RL checkpoint round trip, 3. bare state dict
+    ck = CK.allenact_checkpoint(sd, total_steps=7)
+    assert CK.detect_format(ck) == "allenact" and ck["total_steps"] == 7
+    back = CK.to_model_state_dict(ck)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    assert CK.detect_format(sd) == "bare" and set(CK.to_model_state_dict(sd)) == set(sd)
+    assert not any("critic_tsfm" in k for k in CK.strip_critic_towers(sd))
+    with pytest.raises(ValueError):
+        CK.detect_format({"weights": 1})
