@@ -129,6 +129,15 @@ typedef struct {
 int svla_clip_adam(svla_ctx* ctx, float* p, float* g, float* m, float* v, void* p_bf16, long long n,
                    const float* sq_norm_dev, const svla_adam_hparams* hp, svla_stream stream);
 
+/* HL-Gauss discrete-critic loss fwd+bwd (utils/loss_functions.py:7-30; read-out of DiscreteCriticHead,
+ * allenact_dino_transformer.py:743-766): logits [R, num_bins] (row stride ldl), target [R], support
+ * [num_bins + 1] = the module's torch.linspace(min, max, num_bins + 1).  out_loss[0] = F.cross_entropy(logits,
+ * transform_to_probs(target)); dlogits (or NULL) = d out_loss / d logits * grad_scale; values (or NULL) [R] =
+ * transform_from_probs(softmax(logits)). */
+int svla_hl_gauss_fwd_bwd(svla_ctx* ctx, const float* logits, long long ldl, const float* target, const float* support,
+                          int num_bins, float sigma, float grad_scale, float* out_loss, float* dlogits, float* values,
+                          long long R, svla_stream stream);
+
 /* ======================================================================================
  * Dense path (tensor-core bound): building blocks of the three towers
  * ====================================================================================== */

@@ -87,6 +87,7 @@ PROTOTYPES: Dict[str, list] = {
                           C.c_float, c_p],
     "svla_attn_cls_bwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, C.c_int, c_p,
                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
+    "svla_hl_gauss_fwd_bwd": [c_p, c_p, c_ll, c_p, c_p, C.c_int, C.c_float, C.c_float, c_p, c_p, c_p, c_ll, c_p],
     "svla_attn_decode": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_ll, c_p, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.c_int,
                          C.c_int, C.c_float, c_p],
     "svla_swiglu_fwd": [c_p, c_p, c_p, C.c_int, c_ll, C.c_int, c_p],

@@ -159,3 +159,57 @@ class PPOValue(AbstractActorCriticLoss):
 class SafePPOValue(PPOValue):
     """Fork's cost-critic twin of PPOValue on (c_values, c_returns)."""
     _cost = True
+
+
+class _HLGaussFn(torch.autograd.Function):
+    """One fused launch computes the loss and d loss / d logits; backward only scales by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, target, support, sigma):
+        loss, dl, _ = ops.hl_gauss_fwd_bwd(logits.contiguous(), target, support, sigma)
+        ctx.save_for_backward(dl)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None, None
+
+
+class HLGaussLoss(torch.nn.Module):
+    """utils/loss_functions.py:7-30 -- the discrete-critic loss behind `critic_type="discrete"`
+    (allenact_dino_transformer.py:743-766).  Same constructor, `forward(logits, target)`, `transform_to_probs`
+    and `transform_from_probs`; `forward` and `values_from_logits` run the fused sm_100a kernel
+    (`svla_hl_gauss_fwd_bwd`), the two transform_* helpers are the reference's tensor expressions (they are not on
+    the update path: the fused kernel builds the soft targets itself)."""
+
+    def __init__(self, min_value: float, max_value: float, num_bins: int, sigma: float):
+        super().__init__()
+        self.min_value, self.max_value, self.num_bins, self.sigma = min_value, max_value, num_bins, sigma
+        self.support = torch.linspace(min_value, max_value, num_bins + 1, dtype=torch.float32)
+
+    def _support(self, device):
+        if self.support.device != device:
+            self.support = self.support.to(device)
+        return self.support
+
+    def forward(self, logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        lg = logits.reshape(-1, logits.shape[-1]).float()
+        return _HLGaussFn.apply(lg, target.reshape(-1).float(), self._support(logits.device), self.sigma)
+
+    def values_from_logits(self, logits: torch.Tensor) -> torch.Tensor:
+        """DiscreteCriticHead's value read-out: transform_from_probs(softmax(logits)) in the same fused kernel."""
+        lg = logits.reshape(-1, logits.shape[-1]).float().contiguous()
+        _, _, vals = ops.hl_gauss_fwd_bwd(lg, torch.zeros(lg.shape[0], device=lg.device), self._support(lg.device),
+                                          self.sigma, want_grad=False, want_values=True)
+        return vals.view(logits.shape[:-1])
+
+    def transform_to_probs(self, target: torch.Tensor) -> torch.Tensor:
+        sup = self._support(target.device)
+        cdf = torch.special.erf((sup - target.unsqueeze(-1)) / (torch.sqrt(torch.tensor(2.0)) * self.sigma))
+        z = cdf[..., -1] - cdf[..., 0]
+        return (cdf[..., 1:] - cdf[..., :-1]) / z.unsqueeze(-1)
+
+    def transform_from_probs(self, probs: torch.Tensor) -> torch.Tensor:
+        sup = self._support(probs.device)
+        return torch.sum(probs * ((sup[:-1] + sup[1:]) / 2), dim=-1)

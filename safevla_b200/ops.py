@@ -245,6 +245,19 @@ def attn_cls_bwd(q0, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.12
                                    ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_bwd")
 
 
+def hl_gauss_fwd_bwd(logits, target, support, sigma, grad_scale=1.0, want_grad=True, want_values=False):
+    """logits fp32 [R, B]; target fp32 [R]; support fp32 [B + 1] -> (loss [1], dlogits or None, values or None)."""
+    R, B = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and support.numel() == B + 1
+    loss = torch.empty(1, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    vals = torch.empty(R, device=logits.device) if want_values else None
+    check(_lib().svla_hl_gauss_fwd_bwd(get_ctx(), ptr(logits), logits.stride(0), ptr(target.contiguous()), ptr(support), B,
+                                       float(sigma), float(grad_scale), ptr(loss), ptr(dl), ptr(vals), R, stream_ptr()),
+          "svla_hl_gauss_fwd_bwd")
+    return loss, dl, vals
+
+
 def attn_decode(q, cache_k, cache_v, time_step, pos, o, H=8, dh=64, scale=0.125):
     """q [N, H*dh]; cache_k / cache_v [N, rows, H*dh] holding this step's K / V at row `pos`; time_step int64 [N]."""
     N = q.shape[0]

@@ -292,3 +292,18 @@ def test_checkpoint_format_conversion():
     assert not any("critic_tsfm" in k for k in CK.strip_critic_towers(sd))
     with pytest.raises(ValueError):
         CK.detect_format({"weights": 1})
+
+
+def test_hl_gauss_oracle_reproduces_reference_golden():
+    from oracle.make_golden_hlgauss import inputs
+    for rec in torch.load(os.path.join(GOLDEN_DIR, "hl_gauss.pt"), weights_only=False):
+        c = rec["case"]
+        logits, target = inputs(c)
+        sup = TO.hl_gauss_support(c["vmin"], c["vmax"], c["bins"])
+        assert torch.equal(sup, rec["support"])
+        lg = logits.clone().requires_grad_(True)
+        loss = TO.hl_gauss_loss(lg, target, sup, c["sigma"])
+        loss.backward()
+        assert abs(loss.item() - rec["loss"].item()) < 1e-6 * max(1, abs(rec["loss"].item()))
+        assert relerr(lg.grad, rec["dlogits"]) < 1e-5 and relerr(TO.hl_gauss_value(logits, sup), rec["values"]) < 1e-5
+        assert relerr(TO.hl_gauss_probs(sup, target, c["sigma"]), rec["probs"]) < 1e-6

@@ -1,5 +1,6 @@
 """Per-kernel parity of the C-ABI entry points against torch/oracle references (B200 only)."""
 import math
+import os
 
 import pytest
 import torch
@@ -140,6 +141,27 @@ def test_stage0_value_losses(dev):
     assert abs(scal[0].item() - exp.item()) < 1e-5 * exp.item()
     assert torch.allclose(dv.cpu(), (v - r) / R, rtol=1e-5, atol=1e-9)
     assert torch.allclose(dcv.cpu(), (cv - cr) / R, rtol=1e-5, atol=1e-9)
+
+
+def test_hl_gauss_fused_loss_matches_reference_golden(dev):
+    """Discrete-critic HL-Gauss loss (utils/loss_functions.py:7-30): fused fwd+bwd kernel against the reference's
+    own outputs (tests/golden/hl_gauss.pt) -- loss, d loss / d logits and the value read-out."""
+    from oracle.make_golden_hlgauss import inputs
+    from safevla_b200.losses import HLGaussLoss
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "hl_gauss.pt"), weights_only=False)
+    for rec in gold:
+        c = rec["case"]
+        logits, target = inputs(c)
+        m = HLGaussLoss(c["vmin"], c["vmax"], c["bins"], c["sigma"])
+        lg = logits.to(dev).requires_grad_(True)
+        loss = m(lg, target.to(dev))
+        loss.backward()
+        assert abs(loss.item() - rec["loss"].item()) < 1e-5 * max(1, abs(rec["loss"].item()))
+        assert relerr(lg.grad.cpu(), rec["dlogits"]) < 1e-4
+        vals = m.transform_from_probs(torch.softmax(logits.to(dev), -1))
+        assert relerr(vals.cpu(), rec["values"]) < 1e-5
+        assert relerr(m.values_from_logits(logits.to(dev)).cpu(), rec["values"]) < 1e-5
+        assert relerr(m.transform_to_probs(target.to(dev)).cpu(), rec["probs"]) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------ optimizer / lagrange
