@@ -145,7 +145,8 @@ int svla_hl_gauss_fwd_bwd(svla_ctx* ctx, const float* logits, long long ldl, con
 typedef enum {
   SVLA_EPI_NONE = 0,
   SVLA_EPI_RELU = 1,        /* C = relu(acc + bias) */
-  SVLA_EPI_RELU_MASK = 2    /* C = (acc + bias) * (aux > 0): ReLU backward fused into a dgrad */
+  SVLA_EPI_RELU_MASK = 2,   /* C = (acc + bias) * (aux > 0): ReLU backward fused into a dgrad */
+  SVLA_EPI_GELU = 3         /* C = gelu_erf(acc + bias): DINOv2 MLP (vision preprocessor, forward only) */
 } svla_epilogue;
 
 typedef struct {
@@ -230,11 +231,13 @@ int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, const void* k
 
 /* Single-step decoder attention against the KV cache (rollout-side T = 1 inference; llama/model.py:224-247,279-317,
  * episode-start mask allenact_dino_transformer.py:386-397).  q [N, H*dh] (ldq); cache_k / cache_v [N, cache_rows,
- * H*dh] (row stride ldc) already holding this step's K / V at row `pos`; sampler n attends to rows
- * [max(pos - time_step[n], 0), pos] (time_step NULL: only row pos); o [N, H*dh]. */
+ * H*dh] (row stride ldc) already holding this step's K / V at row `pos`; query n uses cached sequence
+ * n / q_per_cache and attends to its rows [max(pos - time_step[n], 0), pos] (time_step NULL: rows [0, pos]);
+ * o [N, H*dh].  q_per_cache = S with pos = S - 1 is plain unmasked attention over S-token sequences (the fp32
+ * parity path of sequences longer than the shared-memory kernels take). */
 int svla_attn_decode(svla_ctx* ctx, const void* q, long long ldq, const void* cache_k, const void* cache_v,
                      long long cache_rows, long long ldc, const int64_t* time_step, int pos, void* o, long long ldo,
-                     int dtype, int N, int H, int dh, float scale, svla_stream stream);
+                     int dtype, int N, int H, int dh, float scale, int q_per_cache, svla_stream stream);
 
 /* SwiGLU gate (llama/model.py:360): g = silu(a) * b, a|b packed as [rows, 2*F] (w1 | w3 outputs). */
 int svla_swiglu_fwd(svla_ctx* ctx, const void* ab, void* g, int dtype, long long rows, int F, svla_stream stream);
@@ -265,6 +268,19 @@ int svla_copy_rows(svla_ctx* ctx, const void* src, int dtype_src, long long lds,
 /* broadcast one fp32 vector into mapped rows (fusion token): dst[dmap(i), :] = vec */
 int svla_fill_rows(svla_ctx* ctx, const float* vec, void* dst, int dtype_dst, long long ldd, svla_rowmap dmap,
                    long long rows, int D, svla_stream stream);
+
+/* ---- rollout-side vision preprocessor (DINOv2 ViT-S/14; dino_preprocessors.py:20-38,119-125,224-239) ----
+ * uint8 frames [N, H, W, 3] -> normalised, cropped, im2col'd patches [N*PH*PW, Kpad] (bf16 or fp32), the A operand of
+ * the patch-embedding GEMM: column c*patch^2 + dy*patch + dx = (pixel / 255 - mean[c]) / std[c]; mean3 / std3 are HOST
+ * pointers to three floats. */
+int svla_patchify_u8(svla_ctx* ctx, const uint8_t* img, int N, int H, int W, int patch, int crop_left, int crop_right,
+                     const float* mean3, const float* std3, void* out, int dtype, int Kpad, svla_stream stream);
+/* x[n, 0] = cls + pos[0]; x[n, 1 + p] = patches[n*num_patches + p] + pos[1 + p]  (cls, pos fp32) */
+int svla_vit_assemble(svla_ctx* ctx, const void* patches, const float* cls, const float* pos, void* x, int dtype, int N,
+                      int num_patches, int D, svla_stream stream);
+/* AdaptiveAvgPool2d((OH, OW)) over the patch tokens of x [N, 1 + PH*PW, D] -> out fp32 [N, D, OH, OW] */
+int svla_tokens_pool(svla_ctx* ctx, const void* x, int dtype, float* out, int N, int PH, int PW, int D, int OH, int OW,
+                     svla_stream stream);
 
 /* x *= *scale_dev (upstream gradient of the scalar loss applied to the fused kernel's gradients) */
 int svla_scale_by(svla_ctx* ctx, float* x, long long n, const float* scale_dev, svla_stream stream);

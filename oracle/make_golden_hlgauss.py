@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 REF = os.environ.get("SAFEVLA_REFERENCE", "/root/reference")
 
 CASES = [dict(R=64, bins=101, vmin=-10.0, vmax=10.0, sigma=0.75 * 20.0 / 101, seed=5),
-         dict(R=1000, bins=51, vmin=0.0, vmax=25.0, sigma=0.4, seed=6),
+         dict(R=200, bins=51, vmin=0.0, vmax=25.0, sigma=0.4, seed=6),
          dict(R=7, bins=300, vmin=-1.0, vmax=1.0, sigma=0.01, seed=7)]
 
 

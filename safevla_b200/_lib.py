@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsafevla_b200.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_RELU, EPI_RELU_MASK = 0, 1, 2
+EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_GELU = 0, 1, 2, 3
 ATTN_FULL, ATTN_TRAJ_CAUSAL, ATTN_T5_BIAS = 0, 1, 2
 PPO_NSCALARS = 16
 
@@ -87,9 +87,13 @@ PROTOTYPES: Dict[str, list] = {
                           C.c_float, c_p],
     "svla_attn_cls_bwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, C.c_int, c_p,
                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
+    "svla_patchify_u8": [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int,
+                         c_p],
+    "svla_vit_assemble": [c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p],
+    "svla_tokens_pool": [c_p, c_p, C.c_int, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p],
     "svla_hl_gauss_fwd_bwd": [c_p, c_p, c_ll, c_p, c_p, C.c_int, C.c_float, C.c_float, c_p, c_p, c_p, c_ll, c_p],
     "svla_attn_decode": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_ll, c_p, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.c_int,
-                         C.c_int, C.c_float, c_p],
+                         C.c_int, C.c_float, C.c_int, c_p],
     "svla_swiglu_fwd": [c_p, c_p, c_p, C.c_int, c_ll, C.c_int, c_p],
     "svla_swiglu_bwd": [c_p, c_p, c_p, c_p, C.c_int, c_ll, C.c_int, c_p],
     "svla_embed_time_fwd": [c_p, c_p, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ 
                                                           const T* __restrict__ cache_k, const T* __restrict__ cache_v,
                                                           long long cache_rows, long long ldc,
                                                           const int64_t* __restrict__ time_step, int pos,
-                                                          T* __restrict__ o, long long ldo, int N, int H, float scale) {
+                                                          T* __restrict__ o, long long ldo, int N, int H, float scale,
+                                                          int q_per_cache) {
   const int lane = threadIdx.x & 31, r = lane >> 3, c = lane & 7;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)N * H) return;
@@ -54,10 +55,11 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ 
   load8<T>(q + (long long)n * ldq + h * DH + c * 8, qv);
 #pragma unroll
   for (int d = 0; d < 8; ++d) qv[d] *= scale;
-  long long start = (long long)pos - (time_step ? time_step[n] : (long long)pos);
+  long long start = time_step ? (long long)pos - time_step[n] : 0;  // no time_step: every row [0, pos]
   if (start < 0) start = 0;
-  const T* kb = cache_k + (long long)n * cache_rows * ldc + h * DH + c * 8;
-  const T* vb = cache_v + (long long)n * cache_rows * ldc + h * DH + c * 8;
+  const long long cn = n / q_per_cache;  // queries that share one cached sequence (plain attention: S per sequence)
+  const T* kb = cache_k + cn * cache_rows * ldc + h * DH + c * 8;
+  const T* vb = cache_v + cn * cache_rows * ldc + h * DH + c * 8;
   float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
   for (int d = 0; d < 8; ++d) acc[d] = 0.f;
@@ -115,7 +117,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ 
 
 extern "C" int svla_attn_decode(svla_ctx* ctx, const void* q, long long ldq, const void* cache_k, const void* cache_v,
                                 long long cache_rows, long long ldc, const int64_t* time_step, int pos, void* o,
-                                long long ldo, int dtype, int N, int H, int dh, float scale, svla_stream stream) {
+                                long long ldo, int dtype, int N, int H, int dh, float scale, int q_per_cache,
+                                svla_stream stream) {
   SVLA_CHECK_ARG(ctx && q && cache_k && cache_v && o, "NULL argument");
   SVLA_CHECK_ARG(dh == DH, "head dim must be 64");
   SVLA_CHECK_ARG(pos >= 0 && pos < cache_rows, "position outside the cache");
@@ -123,11 +126,12 @@ extern "C" int svla_attn_decode(svla_ctx* ctx, const void* q, long long ldq, con
   SVLA_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(cache_k) |
                    reinterpret_cast<uintptr_t>(cache_v) | reinterpret_cast<uintptr_t>(o)) & 31) == 0,
                  "buffers must be 32-byte aligned");
+  SVLA_CHECK_ARG(q_per_cache >= 1, "q_per_cache must be >= 1");
   if (N <= 0) return SVLA_OK;
   const long long threads = (long long)N * H * 32;
   SVLA_DISPATCH_DTYPE(dtype, T, (attn_decode_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
                                     (const T*)q, ldq, (const T*)cache_k, (const T*)cache_v, cache_rows, ldc, time_step, pos,
-                                    (T*)o, ldo, N, H, scale)));
+                                    (T*)o, ldo, N, H, scale, q_per_cache)));
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }

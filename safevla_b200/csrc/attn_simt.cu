@@ -267,6 +267,16 @@ int svla_attn_tc2_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, con
 int svla_attn_tc2_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
                       const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
                       const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st);
+// attn_flash.cu: S > 256, forward only
+bool svla_attn_flash_supported(int mode, int dtype, int S, int dh, long long ld, long long ldo, const void* q,
+                               const void* k, const void* v, const void* o);
+int svla_attn_flash_fwd(svla_ctx* ctx, const void* q, const void* k, const void* v, long long ld, void* o, long long ldo,
+                        float* lse, int B, int S, int H, float scale, cudaStream_t st);
+extern "C" int svla_attn_decode(svla_ctx* ctx, const void* q, long long ldq, const void* cache_k, const void* cache_v,
+                                long long cache_rows, long long ldc, const int64_t* time_step, int pos, void* o,
+                                long long ldo, int dtype, int N, int H, int dh, float scale, int q_per_cache,
+                                svla_stream stream);
+static inline bool lse_needed_beyond_flash(const float* lse, int dtype) { return lse != nullptr && dtype != SVLA_BF16; }
 static int g_attn_impl = 0;  // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel (error when unsupported)
 extern "C" int svla_set_attn_impl(int impl) {
   g_attn_impl = impl;
@@ -278,10 +288,19 @@ extern "C" int svla_attn_fwd(svla_ctx* ctx, int mode, const void* q, const void*
                              const int64_t* keymask, int B, int S, int H, int dh, float scale, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && q && k && v && o, "NULL argument");
   SVLA_CHECK_ARG(dh == DH, "head dim must be 64");
-  SVLA_CHECK_ARG(S >= 1 && S <= kMaxS, "S must be in [1, 256]");
+  SVLA_CHECK_ARG(S >= 1, "S must be >= 1");
   SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
   SVLA_CHECK_ARG(ld % 4 == 0 && ldo % 4 == 0, "leading dims must be multiples of 4");
   if (B <= 0) return SVLA_OK;
+  if (S > kMaxS) {
+    // longer than the single-/two-tile kernels take (the vision preprocessor's 257- / 433-token ViT blocks):
+    // unmasked forward only -- tcgen05 flash kernel for bf16, the warp-per-query cache kernel otherwise
+    SVLA_CHECK_ARG(mode == SVLA_ATTN_FULL && !lse_needed_beyond_flash(lse, dtype), "S > 256: unmasked forward without lse (bf16: lse available)");
+    if (g_attn_impl != 1 && svla_attn_flash_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o))
+      return svla_attn_flash_fwd(ctx, q, k, v, ld, o, ldo, lse, B, S, H, scale, as_stream(stream));
+    SVLA_CHECK_ARG(lse == nullptr, "S > 256 on the CUDA-core path does not produce lse");
+    return svla_attn_decode(ctx, q, ld, k, v, S, ld, nullptr, S - 1, o, ldo, dtype, B * S, H, dh, scale, S, stream);
+  }
   {
     const bool tc2_ok = svla_attn_tc2_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o);
     if (tc2_ok && g_attn_impl != 1)

@@ -80,6 +80,9 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// exact (erf) GELU, nn.GELU() default -- the DINOv2 MLP activation
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

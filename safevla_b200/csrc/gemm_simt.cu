@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
       v *= d.alpha;
       if (d.bias) v += __ldg(d.bias + n);
       if (d.epilogue == SVLA_EPI_RELU) v = fmaxf(v, 0.f);
+    else if (d.epilogue == SVLA_EPI_GELU) v = gelu_erf(v);
+      else if (d.epilogue == SVLA_EPI_GELU) v = gelu_erf(v);
       else if (d.epilogue == SVLA_EPI_RELU_MASK) v = (ld_any(d.aux, d.dtypeAux, (long long)m * d.ldaux + n) > 0.f) ? v : 0.f;
       if (d.residual) v += ld_any(d.residual, d.dtypeR, (long long)m * d.ldr + n);
       const long long ci = (long long)m * d.ldc + n;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmArgs g) {
     v *= d.alpha;
     if (d.bias) v += __ldg(d.bias + n);
     if (d.epilogue == SVLA_EPI_RELU) v = fmaxf(v, 0.f);
+    else if (d.epilogue == SVLA_EPI_GELU) v = gelu_erf(v);
     else if (d.epilogue == SVLA_EPI_RELU_MASK) v = (ld_any(d.aux, d.dtypeAux, (long long)m * d.ldaux + n) > 0.f) ? v : 0.f;
     if (d.residual) v += ld_any(d.residual, d.dtypeR, (long long)m * d.ldr + n);
     const long long ci = (long long)m * d.ldc + n;

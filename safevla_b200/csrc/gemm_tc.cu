@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(TcArgs g) {
     v *= g.alpha;
     if (g.bias) v += __ldg(g.bias + n);
     if (g.epilogue == SVLA_EPI_RELU) v = fmaxf(v, 0.f);
+    else if (g.epilogue == SVLA_EPI_GELU) v = gelu_erf(v);
     else if (g.epilogue == SVLA_EPI_RELU_MASK) v = ld_elem(g.aux, g.dtypeAux, (long long)m * g.ldaux + n) > 0.f ? v : 0.f;
     if (g.residual) v += ld_elem(g.residual, g.dtypeR, (long long)m * g.ldr + n);
     const long long ci = (long long)m * g.ldc + n;

@@ -240,6 +240,7 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
         float x2 = __uint_as_float(r[4 * e + 2]) * g.alpha, x3 = __uint_as_float(r[4 * e + 3]) * g.alpha;
         if (g.bias) { x0 += bias4[e].x; x1 += bias4[e].y; x2 += bias4[e].z; x3 += bias4[e].w; }
         if (g.epilogue == SVLA_EPI_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+        else if (g.epilogue == SVLA_EPI_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
         r[4 * e] = __float_as_uint(x0); r[4 * e + 1] = __float_as_uint(x1);
         r[4 * e + 2] = __float_as_uint(x2); r[4 * e + 3] = __float_as_uint(x3);
       }
@@ -341,6 +342,9 @@ __device__ __forceinline__ void epilogue_direct(const TcArgs& g, uint32_t taddr,
       if (g.epilogue == SVLA_EPI_RELU) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+      } else if (g.epilogue == SVLA_EPI_GELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
       } else if (g.epilogue == SVLA_EPI_RELU_MASK) {
         float a[8];
         ld8(g.aux, g.dtypeAux, (long long)m * g.ldaux + n0 + j, a);

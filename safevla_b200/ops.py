@@ -245,6 +245,30 @@ def attn_cls_bwd(q0, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.12
                                    ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_bwd")
 
 
+def patchify_u8(img, out, patch, crop_left, crop_right, mean, std):
+    """img uint8 [N, H, W, 3] (device) -> out [N*PH*PW, Kpad]; mean / std: 3 python floats."""
+    N, H, W, _ = img.shape
+    assert img.dtype == torch.uint8 and img.is_contiguous() and out.is_contiguous()
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    check(_lib().svla_patchify_u8(get_ctx(), ptr(img), N, H, W, patch, crop_left, crop_right, m3, s3, ptr(out), dt(out),
+                                  out.shape[1], stream_ptr()), "svla_patchify_u8")
+    return out
+
+
+def vit_assemble(patches, cls, pos, x, N, num_patches):
+    D = patches.shape[-1]
+    check(_lib().svla_vit_assemble(get_ctx(), ptr(patches), ptr(cls), ptr(pos), ptr(x), dt(x), N, num_patches, D,
+                                   stream_ptr()), "svla_vit_assemble")
+    return x
+
+
+def tokens_pool(x, out, N, PH, PW, OH, OW):
+    D = x.shape[-1]
+    check(_lib().svla_tokens_pool(get_ctx(), ptr(x), dt(x), ptr(out), N, PH, PW, D, OH, OW, stream_ptr()),
+          "svla_tokens_pool")
+    return out
+
+
 def hl_gauss_fwd_bwd(logits, target, support, sigma, grad_scale=1.0, want_grad=True, want_values=False):
     """logits fp32 [R, B]; target fp32 [R]; support fp32 [B + 1] -> (loss [1], dlogits or None, values or None)."""
     R, B = logits.shape
@@ -265,7 +289,7 @@ def attn_decode(q, cache_k, cache_v, time_step, pos, o, H=8, dh=64, scale=0.125)
     assert cache_k.stride(0) == cache_k.shape[1] * cache_k.stride(1)
     check(_lib().svla_attn_decode(get_ctx(), ptr(q), q.stride(0), ptr(cache_k), ptr(cache_v), cache_k.shape[1],
                                   cache_k.stride(1), ptr(time_step), int(pos), ptr(o), o.stride(0), dt(q), N, H, dh,
-                                  scale, stream_ptr()), "svla_attn_decode")
+                                  scale, 1, stream_ptr()), "svla_attn_decode")
     return o
 
 

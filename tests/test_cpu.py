@@ -307,3 +307,24 @@ def test_hl_gauss_oracle_reproduces_reference_golden():
         assert abs(loss.item() - rec["loss"].item()) < 1e-6 * max(1, abs(rec["loss"].item()))
         assert relerr(lg.grad, rec["dlogits"]) < 1e-5 and relerr(TO.hl_gauss_value(logits, sup), rec["values"]) < 1e-5
         assert relerr(TO.hl_gauss_probs(sup, target, c["sigma"]), rec["probs"]) < 1e-6
+
+
+# ------------------------------------------------------------------ vision preprocessor
+def test_vit_oracle_reproduces_hf_golden_and_layouts_agree():
+    from oracle import vit_oracle as VO
+    from oracle.make_golden_vit import frames
+    from safevla_b200.vision import hub_to_canonical, interpolate_pos_embed
+    torch.set_num_threads(os.cpu_count() or 1)
+    for rec in torch.load(os.path.join(GOLDEN_DIR, "dinov2_vits14.pt"), weights_only=False):
+        c = rec["case"]
+        sd = VO.init_hub_state_dict(c["wseed"])
+        out = VO.dino_preprocess(sd, frames(c), c["crop"])
+        assert out.shape == rec["out"].shape == (c["N"], 384, 7, 12)
+        assert relerr(out, rec["out"]) < 1e-4
+    # the product's weight loader sees the same canonical tensors from the hub and the HuggingFace layouts
+    sd = VO.init_hub_state_dict(5)
+    a, b = hub_to_canonical(sd), hub_to_canonical(VO.hub_to_hf(sd))
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    pos = interpolate_pos_embed(a["pos"], 16, 27)
+    assert pos.shape == (1 + 16 * 27, 384) and torch.equal(pos[0], a["pos"][0])
+    assert torch.equal(interpolate_pos_embed(a["pos"], 37, 37), a["pos"])

@@ -399,6 +399,56 @@ def test_attention_decode_kv_cache(dev, N, pos, rows, dt_):
     assert relerr(o.float(), ref) < (2e-5 if dt_ == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("S,B,H", [(433, 3, 6), (257, 5, 6), (300, 2, 8), (1024, 1, 6)])
+def test_attention_flash_long_sequences(dev, S, B, H):
+    """S > 256 (vision preprocessor): tcgen05 flash forward (bf16) and the CUDA-core path (fp32) against torch."""
+    D = H * 64
+    g = torch.Generator().manual_seed(S)
+    qkv32 = (torch.randn(B * S, 3 * D, generator=g) * 0.6).to(dev)
+    for dt_, tol in ((torch.bfloat16, 2e-2), (torch.float32, 2e-5)):
+        qkv = qkv32.to(dt_)
+        o = torch.empty(B * S, D, device=dev, dtype=dt_)
+        lse = torch.empty(B * H * S, device=dev) if dt_ == torch.bfloat16 else None
+        _ops().attn_fwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, lse, B, S, H=H)
+        q, k, v = [qkv[:, i * D:(i + 1) * D].float().view(B, S, H, 64).transpose(1, 2) for i in range(3)]
+        sc = q @ k.transpose(-1, -2) * 0.125
+        ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, D)
+        assert relerr(o.float(), ref) < tol, (dt_, relerr(o.float(), ref))
+        if lse is not None:
+            assert (lse.view(B, H, S) - torch.logsumexp(sc, -1)).abs().max().item() < 2e-2
+
+
+def test_vit_glue_kernels(dev):
+    """patchify (normalise + crop + im2col), token assembly, adaptive pooling, GELU epilogue."""
+    g = torch.Generator().manual_seed(0)
+    N, H, W, P = 3, 28, 48, 14
+    img = torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev)
+    mean, std = (0.48, 0.45, 0.40), (0.26, 0.27, 0.28)
+    out = torch.full((N * 2 * 3, 592), 7.0, device=dev)
+    _ops().patchify_u8(img, out, P, 3, 3, mean, std)
+    x = (img.permute(0, 3, 1, 2).float() / 255 - torch.tensor(mean, device=dev).view(1, 3, 1, 1)) / torch.tensor(std, device=dev).view(1, 3, 1, 1)
+    ref = torch.nn.functional.unfold(x[:, :, :, 3:-3], kernel_size=P, stride=P).transpose(1, 2).reshape(N * 6, 588)
+    assert torch.allclose(out[:, :588], ref, rtol=1e-6, atol=1e-6) and out[:, 588:].abs().max() == 0
+    D, Np = 384, 6
+    patches, cls, pos = torch.randn(N * Np, D, device=dev), torch.randn(D, device=dev), torch.randn(Np + 1, D, device=dev)
+    xt = _ops().vit_assemble(patches, cls, pos, torch.empty(N * (Np + 1), D, device=dev), N, Np)
+    exp = torch.cat([cls.expand(N, 1, D), patches.view(N, Np, D)], 1) + pos
+    assert torch.equal(xt.view(N, Np + 1, D), exp)
+    PH, PW = 16, 27
+    tok = torch.randn(N * (PH * PW + 1), D, device=dev)
+    pooled = _ops().tokens_pool(tok, torch.empty(N, D, 7, 12, device=dev), N, PH, PW, 7, 12)
+    grid = tok.view(N, PH * PW + 1, D)[:, 1:].permute(0, 2, 1).reshape(N, D, PH, PW)
+    assert torch.allclose(pooled, torch.nn.functional.adaptive_avg_pool2d(grid, (7, 12)), rtol=1e-5, atol=1e-6)
+    for dt_, impl in ((torch.float32, 1), (torch.bfloat16, 2)):
+        A = (torch.randn(512, 384, generator=g) * 0.5).to(dev, dt_)
+        Bm = (torch.randn(1536, 384, generator=g) * 0.1).to(dev, dt_)
+        bias = torch.randn(1536, generator=g).to(dev)
+        o = torch.empty(512, 1536, device=dev, dtype=dt_)
+        _ops().gemm(A, Bm, o, trans_b=True, bias=bias, epilogue=_L().EPI_GELU, impl=impl)
+        refg = torch.nn.functional.gelu(A.double() @ Bm.double().t() + bias.double())
+        assert relerr(o, refg) < (1e-5 if dt_ == torch.float32 else 1e-2)
+
+
 # ------------------------------------------------------------------------------------------ glue
 def test_swiglu(dev):
     rows, F = 300, 1536

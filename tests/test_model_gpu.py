@@ -227,3 +227,23 @@ def test_sampler_select_keeps_cache_rows(dev):
     b = run(10 ** 9, 6)      # never drop
     for t in range(3, 6):
         assert torch.allclose(a[t], b[t][:, [0, 2]], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ vision preprocessor
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_dino_preprocessor_matches_hf_golden(dev, precision):
+    """uint8 frames -> [N, 384, 7, 12] DINOv2 ViT-S/14 features (dino_preprocessors.py:20-38,119-125,224-239) against
+    the HuggingFace Dinov2Model golden (tests/golden/dinov2_vits14.pt); hub and HF weight layouts both load."""
+    from oracle import vit_oracle as VO
+    from oracle.make_golden_vit import frames
+    from safevla_b200.vision import B200DinoViTPreprocessor
+    for rec in torch.load(os.path.join(GOLDEN_DIR, "dinov2_vits14.pt"), weights_only=False):
+        c = rec["case"]
+        sd = VO.init_hub_state_dict(c["wseed"])
+        if c["name"].endswith("224x224"):
+            sd = VO.hub_to_hf(sd)  # exercise the HuggingFace layout too
+        pre = B200DinoViTPreprocessor("raw_navigation_camera", sd, precision=precision, device=dev, crop=c["crop"])
+        out = pre.process({"raw_navigation_camera": frames(c).to(dev)})
+        assert out.shape == rec["out"].shape and out.dtype == torch.float32
+        tol = 1e-4 if precision == "fp32" else 5e-2  # bf16 operands through 12 blocks, fp32 accumulation
+        assert relerr(out, rec["out"]) < tol, relerr(out, rec["out"])
