@@ -155,10 +155,20 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool part = g.splits > 1;
+    const int dtC = part ? (int)SVLA_F32 : g.dtypeC;
+    const bool staged = (!g.residual || g.dtypeR == dtC) && (!g.aux || g.dtypeAux == dtC);
+    const int cb = half * (BN / 2), ce = cb + BN / 2;
+    SidePre pre;
+    pre.valid = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tn = w % g.tiles_n, tm = (w / g.tiles_n) % g.tiles_m, sp = w / (g.tiles_n * g.tiles_m);
       const int m = tm * BM + q * 32 + lane;
       const bool row_ok = m < g.M;
+      const int wn = w + gridDim.x;  // the tile this warp drains next: its side operand is requested early
+      const int next_m0 = wn < total_work ? ((wn / g.tiles_n) % g.tiles_m) * BM + q * 32 : -1;
+      const int next_nt0 = (wn % g.tiles_n) * BN;
+      if (staged && g.dbg == 0) side_prefetch_first(pre, g, tm * BM + q * 32, tn * BN + cb, lane);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (g.dbg == 1) {
@@ -174,15 +184,13 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         if (keep == 0x12345678u) reinterpret_cast<uint32_t*>(g.C)[0] = keep;
       } else {
-        const bool part = g.splits > 1;
-        const int dtC = part ? (int)SVLA_F32 : g.dtypeC;
-        const bool staged = (!g.residual || g.dtypeR == dtC) && (!g.aux || g.dtypeAux == dtC);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        const int cb = half * (BN / 2), ce = cb + BN / 2;
         uint8_t* stg = stage_base + (warp - kEpiWarp0) * kStgBytes;
         if (!staged) epilogue_direct(g, taddr, m, row_ok, tn * BN, cb, ce, sp);
-        else if (dtC == SVLA_F32) epilogue_staged_t<true>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane);
-        else epilogue_staged_t<false>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane);
+        else if (dtC == SVLA_F32)
+          epilogue_staged_t<true>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane, pre, next_m0, next_nt0);
+        else
+          epilogue_staged_t<false>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane, pre, next_m0, next_nt0);
       }
       tc_fence_before();
       __syncwarp();

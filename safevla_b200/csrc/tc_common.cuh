@@ -153,6 +153,14 @@ __device__ __forceinline__ void st8(void* p, int dt, long long i, const float* v
 // operand, accumulate) is then a run of full 32-byte sectors along a row.
 constexpr int kStgBytes = 32 * 128;  // per epilogue warp
 
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr) : "memory");
+  return u;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
 template <bool F32> __device__ __forceinline__ int stg_off(int row, int slot) {
   return F32 ? row * 128 + ((slot ^ (row & 7)) << 4) : row * 64 + ((slot ^ ((row >> 1) & 3)) << 4);
 }
@@ -164,8 +172,8 @@ __device__ __forceinline__ void stage_in(uint8_t* stg, const void* base, long lo
   for (int p = 0; p < 32 / RPP; ++p) {
     const int row = p * RPP + lane / LPR, slot = lane % LPR;
     if (m0 + row < M)
-      *reinterpret_cast<uint4*>(stg + stg_off<F32>(row, slot)) = __ldg(reinterpret_cast<const uint4*>(
-          reinterpret_cast<const uint8_t*>(base) + (long long)(m0 + row) * ld_bytes + col_bytes + slot * 16));
+      sts128(smem_u32(stg) + stg_off<F32>(row, slot), __ldg(reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint8_t*>(base) + (long long)(m0 + row) * ld_bytes + col_bytes + slot * 16)));
   }
   __syncwarp();
 }
@@ -179,14 +187,14 @@ __device__ __forceinline__ void stage_out(const uint8_t* stg, void* base, long l
     const int row = p * RPP + lane / LPR, slot = lane % LPR;
     if (m0 + row < M)
       *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(base) + (long long)(m0 + row) * ld_bytes + col_bytes +
-                                slot * 16) = *reinterpret_cast<const uint4*>(stg + stg_off<F32>(row, slot));
+                                slot * 16) = lds128(smem_u32(stg) + stg_off<F32>(row, slot));
   }
   __syncwarp();
 }
 // 16-byte slot j of this lane's staged row -> floats (4 for fp32, 8 for bf16)
 template <bool F32>
-__device__ __forceinline__ void piece_load(const uint8_t* stg, int lane, int j, float* o) {
-  const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off<F32>(lane, j));
+__device__ __forceinline__ void piece_load(uint32_t stg_s, int lane, int j, float* o) {
+  const uint4 u = lds128(stg_s + stg_off<F32>(lane, j));
   if (F32) {
     o[0] = __uint_as_float(u.x); o[1] = __uint_as_float(u.y); o[2] = __uint_as_float(u.z); o[3] = __uint_as_float(u.w);
   } else {
@@ -199,25 +207,93 @@ __device__ __forceinline__ void piece_load(const uint8_t* stg, int lane, int j, 
   }
 }
 
+
+// ---- side-operand prefetch ------------------------------------------------------------------------------
+// The ReLU-mask operand / residual tile does not depend on the accumulator, so its global loads are issued one
+// 32-column chunk ahead of their use (across tile boundaries too, and for the first tile before the wait for the
+// accumulator): the epilogue no longer exposes a DRAM round trip per chunk.  (Two chunks ahead was measured slower:
+// the extra registers spill.)  Only the first side operand in application order (aux, residual) of bf16 tiles is
+// prefetched; anything else takes the synchronous stage_in path.
+struct SidePre {
+  uint4 v[4];  // this lane's 16-byte pieces of the next chunk to be consumed
+  int valid;
+};
+__device__ __forceinline__ int side_pick(const TcArgs& g, const void** base, long long* ld) {
+  if (g.splits > 1 || g.dtypeC != SVLA_BF16) return 0;
+  if (g.epilogue == SVLA_EPI_RELU_MASK && g.aux) { *base = g.aux; *ld = g.ldaux; return 1; }
+  if (g.residual) { *base = g.residual; *ld = g.ldr; return 2; }
+  return 0;
+}
+// bf16 chunk [32 rows x 64 B]: lane covers rows (lane / 4) + 8 p, 16-byte slot lane % 4
+__device__ __forceinline__ void side_fetch(uint4* v, const void* base, long long ld_bytes, long long col_bytes, int m0,
+                                           int M, int lane) {
+  const uint8_t* p0 = reinterpret_cast<const uint8_t*>(base) + (long long)(m0 + (lane >> 2)) * ld_bytes + col_bytes +
+                      (lane & 3) * 16;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (m0 + (lane >> 2) + 8 * p < M) v[p] = __ldg(reinterpret_cast<const uint4*>(p0 + (long long)(8 * p) * ld_bytes));
+    else v[p] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void side_commit(uint32_t stg_s, const uint4* v, int lane) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) sts128(stg_s + stg_off<false>(p * 8 + (lane >> 2), lane & 3), v[p]);
+  __syncwarp();
+}
+// chunk 0 of a warp's first tile, issued by the caller BEFORE it waits for the accumulator
+__device__ __forceinline__ void side_prefetch_first(SidePre& pre, const TcArgs& g, int m0, int n0, int lane) {
+  const void* base = nullptr;
+  long long ld = 0;
+  if (pre.valid || !side_pick(g, &base, &ld) || n0 >= g.N) return;
+  side_fetch(pre.v, base, ld * 2, (long long)n0 * 2, m0, g.M, lane);
+  pre.valid = 1;
+}
+
 // columns [c_begin, c_end) of the tile for the 32 rows starting at m0
-template <bool F32>
-__device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtensorMap* mapC, uint8_t* stg0, uint32_t taddr,
-                                                  int m0, int ntile0, int c_begin, int c_end, int sp, int lane) {
+// (next_m0, next_ntile0): the tile this warp drains next (next_m0 < 0: none) -- its first side-operand chunk is
+// requested while the last chunk of this tile is processed.
+//
+// The per-chunk instruction stream of the epilogue warps (LDTM -> math -> pack -> staging -> TMA store, four chunks
+// per warp and tile) is what paces the K = 512 GEMMs, so the flag tests are folded at compile time: EPI >= 0
+// instantiates exactly one combination (epilogue kind, bias, residual, accumulate); EPI = -1 is the run-time
+// generic version for everything else.  For bf16 outputs ReLU and the ReLU mask act on the packed bf16 pairs
+// (one HMNMX2 / HSET2 + LOP per two elements; identical results: rounding to bf16 preserves sign and zero).
+template <bool F32, int EPI, bool BIAS, bool RES, bool ACC>
+__device__ __forceinline__ void epilogue_staged_impl(const TcArgs& g, const CUtensorMap* mapC, uint8_t* stg0, uint32_t taddr,
+                                                     int m0, int ntile0, int c_begin, int c_end, int sp, int lane,
+                                                     SidePre& pre, int next_m0, int next_ntile0) {
+  constexpr bool GEN = EPI < 0;
   constexpr int EP = F32 ? 4 : 8;    // elements per 16-byte slot
   constexpr int NS = F32 ? 8 : 4;    // slots per 32-column row
   constexpr int ES = F32 ? 4 : 2;
   const bool part = g.splits > 1;
+  const int epi = GEN ? g.epilogue : EPI;
+  const bool has_bias = GEN ? (g.bias != nullptr) : BIAS;
+  const bool has_res = GEN ? (g.residual != nullptr) : RES;
+  const bool has_acc = GEN ? (g.accumulate != 0) : ACC;
   uint8_t* Cb = part ? reinterpret_cast<uint8_t*>(g.ws + (size_t)sp * g.M * g.N) : reinterpret_cast<uint8_t*>(g.C);
   const long long ldc_b = (part ? (long long)g.N : g.ldc) * ES;
   // bf16 tiles are 2 KB: two staging buffers per warp, so a TMA store can still be reading one while the next
   // chunk fills the other; fp32 tiles (4 KB) use the single buffer
   constexpr int kBufs = F32 ? 1 : 2;
   int chunk = 0;
+  const void* side_base = nullptr;
+  long long side_ld = 0;
+  int side = 0;
+  if (!F32) {
+    if (GEN) side = side_pick(g, &side_base, &side_ld);
+    else if (EPI == SVLA_EPI_RELU_MASK) { side = 1; side_base = g.aux; side_ld = g.ldaux; }
+    else if (RES) { side = 2; side_base = g.residual; side_ld = g.ldr; }
+  }
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk) {
     const int n0 = ntile0 + c0;
-    if (n0 >= g.N) break;  // warp-uniform
+    if (n0 >= g.N) {  // warp-uniform
+      pre.valid = 0;
+      break;
+    }
     uint8_t* stg = stg0 + (kBufs == 2 ? (chunk & 1) * 2048 : 0);
+    const uint32_t stg_s = smem_u32(stg);
     if (g.tma_store) {  // the bulk store that last read this buffer must have finished reading it
       if (lane == 0) {
         if (kBufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -225,54 +301,73 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
       }
       __syncwarp();
     }
-    float4 bias4[8];
-    if (!part && g.bias) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) bias4[e] = __ldg(reinterpret_cast<const float4*>(g.bias + n0) + e);
-    }
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);
-    tmem_wait_ld();
-    if (!part) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float x0 = __uint_as_float(r[4 * e]) * g.alpha, x1 = __uint_as_float(r[4 * e + 1]) * g.alpha;
-        float x2 = __uint_as_float(r[4 * e + 2]) * g.alpha, x3 = __uint_as_float(r[4 * e + 3]) * g.alpha;
-        if (g.bias) { x0 += bias4[e].x; x1 += bias4[e].y; x2 += bias4[e].z; x3 += bias4[e].w; }
-        if (g.epilogue == SVLA_EPI_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-        else if (g.epilogue == SVLA_EPI_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
-        r[4 * e] = __float_as_uint(x0); r[4 * e + 1] = __float_as_uint(x1);
-        r[4 * e + 2] = __float_as_uint(x2); r[4 * e + 3] = __float_as_uint(x3);
+    if (side) {  // this chunk's side operand: registers -> staging; then request the next chunk of the stream
+      if (!pre.valid) side_fetch(pre.v, side_base, side_ld * ES, (long long)n0 * ES, m0, g.M, lane);  // cold start
+      side_commit(stg_s, pre.v, lane);
+      pre.valid = 0;
+      if (c0 + 32 < c_end && n0 + 32 < g.N) {
+        side_fetch(pre.v, side_base, side_ld * ES, (long long)(n0 + 32) * ES, m0, g.M, lane);
+        pre.valid = 1;
+      } else if (next_m0 >= 0 && next_ntile0 + c_begin < g.N) {
+        side_fetch(pre.v, side_base, side_ld * ES, (long long)(next_ntile0 + c_begin) * ES, next_m0, g.M, lane);
+        pre.valid = 1;
       }
-      if (g.epilogue == SVLA_EPI_RELU_MASK) {
-        stage_in<F32>(stg, g.aux, g.ldaux * ES, (long long)n0 * ES, m0, g.M, lane);
+    }
+    // bias of the 32 columns: one coalesced load (lane l holds column l), broadcast by shuffles after the wait --
+    // holding all 32 values per lane costs 31 more registers than the kernel has
+    float bias_l = 0.f;
+    if (!part && has_bias) bias_l = __ldg(g.bias + n0 + lane);
+    tmem_wait_ld();
+    // which ops can run on the packed bf16 pairs after the conversion
+    const bool relu_packed = !F32 && !part && epi == SVLA_EPI_RELU && !has_res && !has_acc;
+    const bool mask_packed = !F32 && !part && epi == SVLA_EPI_RELU_MASK && !has_res && !has_acc;
+    if (!part) {
+      if (g.alpha != 1.f) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * g.alpha);
+      }
+      if (has_bias) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          r[e] = __float_as_uint(__uint_as_float(r[e]) + __shfl_sync(0xffffffffu, bias_l, e));
+      }
+      if (epi == SVLA_EPI_RELU && !relu_packed) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(fmaxf(__uint_as_float(r[e]), 0.f));
+      } else if (epi == SVLA_EPI_GELU) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(gelu_erf(__uint_as_float(r[e])));
+      } else if (epi == SVLA_EPI_RELU_MASK && !mask_packed) {
+        if (side != 1) stage_in<F32>(stg, g.aux, g.ldaux * ES, (long long)n0 * ES, m0, g.M, lane);
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
           float a[EP];
-          piece_load<F32>(stg, lane, j, a);
+          piece_load<F32>(stg_s, lane, j, a);
 #pragma unroll
           for (int e = 0; e < EP; ++e)
             if (!(a[e] > 0.f)) r[j * EP + e] = 0u;
         }
         __syncwarp();
       }
-      if (g.residual) {
-        stage_in<F32>(stg, g.residual, g.ldr * ES, (long long)n0 * ES, m0, g.M, lane);
+      if (has_res) {
+        if (side != 2) stage_in<F32>(stg, g.residual, g.ldr * ES, (long long)n0 * ES, m0, g.M, lane);
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
           float a[EP];
-          piece_load<F32>(stg, lane, j, a);
+          piece_load<F32>(stg_s, lane, j, a);
 #pragma unroll
           for (int e = 0; e < EP; ++e) r[j * EP + e] = __float_as_uint(__uint_as_float(r[j * EP + e]) + a[e]);
         }
         __syncwarp();
       }
-      if (g.accumulate) {
+      if (has_acc) {
         stage_in<F32>(stg, g.C, ldc_b, (long long)n0 * ES, m0, g.M, lane);
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
           float a[EP];
-          piece_load<F32>(stg, lane, j, a);
+          piece_load<F32>(stg_s, lane, j, a);
 #pragma unroll
           for (int e = 0; e < EP; ++e) r[j * EP + e] = __float_as_uint(__uint_as_float(r[j * EP + e]) + a[e]);
         }
@@ -289,15 +384,28 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           h[e] = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+        if (relu_packed) {
+          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], z);
+        }
+        if (mask_packed) {  // the side operand of this slot sits where the output goes: read it, then overwrite
+          const uint4 a = lds128(stg_s + stg_off<false>(lane, j));
+          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+          u.x &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a.x), z);
+          u.y &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a.y), z);
+          u.z &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a.z), z);
+          u.w &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a.w), z);
+        }
       }
-      *reinterpret_cast<uint4*>(stg + stg_off<F32>(lane, j)) = u;
+      sts128(stg_s + stg_off<F32>(lane, j), u);
     }
     if (g.tma_store) {
-      if (g.dbg != 5) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0 && g.dbg != 4 && g.dbg != 5) {
+      if (lane == 0) {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(mapC),
-                     "r"(smem_u32(stg)), "r"(n0), "r"(m0)
+                     "r"(stg_s), "r"(n0), "r"(m0)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -307,6 +415,35 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
   }
   // no wait here: the staging buffers are private to this warp and re-checked at the top of the next chunk, so the
   // caller may release the TMEM accumulator while the last stores are still in flight
+}
+
+// dispatch on the (warp-uniform) flag combination; the listed ones are every combination the towers launch
+template <bool F32>
+__device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtensorMap* mapC, uint8_t* stg0, uint32_t taddr,
+                                                  int m0, int ntile0, int c_begin, int c_end, int sp, int lane,
+                                                  SidePre& pre, int next_m0, int next_ntile0) {
+#define SVLA_EPI_CALL(E, B, R, A) \
+  epilogue_staged_impl<F32, E, B, R, A>(g, mapC, stg0, taddr, m0, ntile0, c_begin, c_end, sp, lane, pre, next_m0, next_ntile0)
+  const bool b = g.bias != nullptr, rs = g.residual != nullptr, ac = g.accumulate != 0;
+  const int e = g.epilogue;
+  if (g.splits > 1) { SVLA_EPI_CALL(SVLA_EPI_NONE, false, false, false); return; }  // partial tiles: raw accumulators
+  if (F32) {
+    if (e == SVLA_EPI_NONE && !b && !rs && ac) SVLA_EPI_CALL(SVLA_EPI_NONE, false, false, true);
+    else if (e == SVLA_EPI_NONE && !b && rs && !ac) SVLA_EPI_CALL(SVLA_EPI_NONE, false, true, false);
+    else if (e == SVLA_EPI_NONE && !b && !rs && !ac) SVLA_EPI_CALL(SVLA_EPI_NONE, false, false, false);
+    else SVLA_EPI_CALL(-1, false, false, false);
+  } else {
+    if (ac) SVLA_EPI_CALL(-1, false, false, false);
+    else if (e == SVLA_EPI_NONE && b && !rs) SVLA_EPI_CALL(SVLA_EPI_NONE, true, false, false);
+    else if (e == SVLA_EPI_RELU && b && !rs) SVLA_EPI_CALL(SVLA_EPI_RELU, true, false, false);
+    else if (e == SVLA_EPI_NONE && b && rs) SVLA_EPI_CALL(SVLA_EPI_NONE, true, true, false);
+    else if (e == SVLA_EPI_RELU_MASK && !b && !rs) SVLA_EPI_CALL(SVLA_EPI_RELU_MASK, false, false, false);
+    else if (e == SVLA_EPI_NONE && !b && rs) SVLA_EPI_CALL(SVLA_EPI_NONE, false, true, false);
+    else if (e == SVLA_EPI_NONE && !b && !rs) SVLA_EPI_CALL(SVLA_EPI_NONE, false, false, false);
+    else if (e == SVLA_EPI_GELU && b && !rs) SVLA_EPI_CALL(SVLA_EPI_GELU, true, false, false);
+    else SVLA_EPI_CALL(-1, false, false, false);
+  }
+#undef SVLA_EPI_CALL
 }
 
 // generic per-thread epilogue (mixed residual / aux dtypes): thread = row, 16-byte accesses

@@ -159,7 +159,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     e0.record()
     check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
     e1.record()
-    PROFILE.setdefault(which, []).append((2.0 * M * N * K, e0, e1))
+    PROFILE.setdefault(which, []).append((2.0 * M * N * K, e0, e1, (M, N, K, int(trans_a), int(trans_b), epilogue,
+                                                                    int(accumulate), str(a.dtype)[6:], str(out.dtype)[6:],
+                                                                    residual is not None, colsum_a is not None)))
     return out
 
 
