@@ -119,7 +119,7 @@ class B200SafeActorCritic(nn.Module):
         self.load_state_dict(state_dict if state_dict is not None
                              else init_state_dict(num_actions, num_cameras, seed), strict=True)
 
-        self.t5 = T5Encoder(self.t5_layout, self.t5_arena)
+        self.t5 = T5Encoder(self.t5_layout, self.t5_arena, self.adt)
         self.towers: List[Tower] = []
         for pre in TOWERS:
             tw = Tower(TowerWeights(self.layout, pre, self.param_arena, self.grad_arena, self.shadow_arena),
@@ -177,6 +177,8 @@ class B200SafeActorCritic(nn.Module):
         """bf16 GEMM-operand copy of the fp32 master weights (refreshed by the fused Adam kernel)."""
         if self.shadow_arena is not None:
             ops.cast_bf16(self.param_arena, self.shadow_arena)
+        if getattr(self, "t5", None) is not None:  # frozen T5: bf16 operand copy + relative-position bias table
+            self.t5.refresh()
 
     def attach_grads(self):
         """(Re)point every trainable parameter's .grad at its slice of the gradient arena."""

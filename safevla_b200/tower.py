@@ -419,17 +419,30 @@ class Tower:
 
 
 class T5Encoder:
-    """Frozen T5-small encoder forward (HF modeling_t5.py) on the C-ABI kernels, fp32
-    activations.  Runs on the *unique* prompts of a rollout, once per rollout, shared by the towers."""
+    """Frozen T5-small encoder forward (HF modeling_t5.py) on the C-ABI kernels.  Runs on the
+    *unique* prompts of a rollout, once per rollout, shared by the towers.  fp32 mode: fp32 everywhere (parity);
+    bf16 mode: bf16 GEMM operands from a bf16 copy of the frozen weights on the tcgen05 kernels, fp32 residual
+    stream and fp32 accumulation -- the same split as the decoder."""
 
-    def __init__(self, layout: T5Layout, arena: torch.Tensor):
+    def __init__(self, layout: T5Layout, arena: torch.Tensor, act_dtype: torch.dtype = torch.float32):
         self.layout, self.arena = layout, arena
         self.dev = arena.device
+        self.adt = act_dtype
+        self.shadow: Optional[torch.Tensor] = None
         self._bias_cache: Dict[int, torch.Tensor] = {}
+        self.refresh()
 
-    def w(self, name, shape=None, count=1):
+    def refresh(self):
+        """Re-derive everything computed from the frozen weights (call after they are loaded)."""
+        self._bias_cache.clear()
+        if self.adt == torch.bfloat16:
+            self.shadow = ops.cast_bf16(self.arena, self.shadow)
+
+    def w(self, name, shape=None, count=1, operand: bool = False):
+        """fp32 master view, or (operand=True, bf16 mode) the bf16 GEMM-operand copy."""
         s = self.layout.slots[name]
-        v = self.arena[s.offset: s.offset + s.numel * count]
+        src = self.shadow if (operand and self.shadow is not None) else self.arena
+        v = src[s.offset: s.offset + s.numel * count]
         return v.view(shape if shape is not None else s.shape)
 
     def position_bias(self, L: int) -> torch.Tensor:
@@ -446,20 +459,21 @@ class T5Encoder:
         """input_ids, attention_mask int64 [U, L] (device) -> last_hidden_state [U*L, 512] fp32."""
         U, L = input_ids.shape
         M = U * L
-        f32 = torch.float32
-        new = lambda *s: torch.empty(*s, device=self.dev, dtype=f32)  # noqa: E731
+        f32, odt = torch.float32, self.adt
+        new = lambda *s, dtype=f32: torch.empty(*s, device=self.dev, dtype=dtype)  # noqa: E731
         x = ops.copy_rows(self.w("shared.weight"), new(M, D), M, D, idx=input_ids.reshape(-1).contiguous())
         bias = self.position_bias(L)
         km = attention_mask.contiguous()
         for i in range(6):
             a = f"encoder.block.{i}.layer.0."
-            y = ops.rmsnorm_fwd(x, self.w(a + "layer_norm.weight"), new(M, D), T5_EPS)
-            qkv = ops.gemm(y, self.w(a + "SelfAttention.q.weight", (3 * D, D), 3), new(M, 3 * D))
-            ao = ops.attn_fwd(ATTN_T5_BIAS, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], new(M, D), None, U, L,
-                              scale=1.0, bias=bias, keymask=km)
-            x = ops.gemm(ao, self.w(a + "SelfAttention.o.weight"), new(M, D), residual=x)
+            y = ops.rmsnorm_fwd(x, self.w(a + "layer_norm.weight"), new(M, D, dtype=odt), T5_EPS)
+            qkv = ops.gemm(y, self.w(a + "SelfAttention.q.weight", (3 * D, D), 3, operand=True), new(M, 3 * D, dtype=odt))
+            ao = ops.attn_fwd(ATTN_T5_BIAS, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], new(M, D, dtype=odt), None,
+                              U, L, scale=1.0, bias=bias, keymask=km)
+            x = ops.gemm(ao, self.w(a + "SelfAttention.o.weight", operand=True), new(M, D), residual=x)
             f = f"encoder.block.{i}.layer.1."
-            y = ops.rmsnorm_fwd(x, self.w(f + "layer_norm.weight"), new(M, D), T5_EPS)
-            hf = ops.gemm(y, self.w(f + "DenseReluDense.wi.weight"), new(M, FF), epilogue=EPI_RELU)
-            x = ops.gemm(hf, self.w(f + "DenseReluDense.wo.weight"), new(M, D), residual=x)
+            y = ops.rmsnorm_fwd(x, self.w(f + "layer_norm.weight"), new(M, D, dtype=odt), T5_EPS)
+            hf = ops.gemm(y, self.w(f + "DenseReluDense.wi.weight", operand=True), new(M, FF, dtype=odt),
+                          epilogue=EPI_RELU)
+            x = ops.gemm(hf, self.w(f + "DenseReluDense.wo.weight", operand=True), new(M, D), residual=x)
         return ops.rmsnorm_fwd(x, self.w("encoder.final_layer_norm.weight"), new(M, D), T5_EPS)
