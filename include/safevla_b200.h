@@ -292,6 +292,14 @@ int svla_cast_bf16(svla_ctx* ctx, const float* x, void* y, long long n, svla_str
  * CPU decode loop at allenact_dino_transformer.py:591-598. */
 int svla_hash_rows(svla_ctx* ctx, const uint8_t* rows, long long R, int L, uint64_t* out, svla_stream stream);
 
+/* Storage-side episode-cost bookkeeping for one environment step (the Jc = mean finished-episode cost that the
+ * Lagrange update consumes; the reference's engine derives it from the task metrics of SafeRLStepResult,
+ * tasks/abstract_task.py:333,369-380): episode_cost[n] += costs[n]; every sampler whose episode ended at this step
+ * (mask_next[n] == 0) adds its episode total to sum_cnt[0], increments sum_cnt[1] and restarts from zero.
+ * Deterministic (one block, fixed order). */
+int svla_episode_cost_step(svla_ctx* ctx, const float* costs, const float* mask_next, float* episode_cost,
+                           float* sum_cnt, int N, svla_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -433,3 +433,39 @@ extern "C" int svla_hash_rows(svla_ctx* ctx, const uint8_t* rows, long long R, i
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
+
+
+// ---- episode-cost bookkeeping of the storage (Jc of the Lagrange update) -------------------------------------------
+// One block, fixed summation order (deterministic): episode_cost[n] += cost[n]; samplers whose episode ended at this
+// step (mask_next[n] == 0) add their episode total to sum_cnt[0], bump sum_cnt[1] and restart at zero.
+__global__ void __launch_bounds__(256) episode_cost_step_kernel(const float* __restrict__ costs,
+                                                                const float* __restrict__ mask_next,
+                                                                float* __restrict__ episode_cost,
+                                                                float* __restrict__ sum_cnt, int N) {
+  __shared__ float red[32];
+  float s = 0.f, c = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float e = episode_cost[n] + costs[n];
+    if (mask_next[n] == 0.f) {
+      s += e;
+      c += 1.f;
+      e = 0.f;
+    }
+    episode_cost[n] = e;
+  }
+  s = block_sum(s, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    sum_cnt[0] += s;
+    sum_cnt[1] += c;
+  }
+}
+
+extern "C" int svla_episode_cost_step(svla_ctx* ctx, const float* costs, const float* mask_next, float* episode_cost,
+                                      float* sum_cnt, int N, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && costs && mask_next && episode_cost && sum_cnt, "NULL argument");
+  if (N <= 0) return SVLA_OK;
+  episode_cost_step_kernel<<<1, 256, 0, as_stream(stream)>>>(costs, mask_next, episode_cost, sum_cnt, N);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}

@@ -362,7 +362,9 @@ int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   const int kb_total = (d->K + BK - 1) / BK;
   int splits = 1;
   const int tiles = g.tiles_m * g.tiles_n;
-  if (tiles * 2 <= ctx->sm_count && kb_total >= 32) {
+  // split K only when K is the batch (row) dimension, i.e. weight-gradient launches: forward / dgrad results then do
+  // not depend on how many rows the launch carries, so a sampler shard reproduces the full batch bit for bit
+  if (d->transA && tiles * 2 <= ctx->sm_count && kb_total >= 32) {
     splits = std::min({ctx->sm_count / tiles, kb_total / 8, 32});
     const size_t per = (size_t)d->M * d->N * sizeof(float);
     splits = (int)std::min<size_t>((size_t)splits, ctx->ws_bytes / std::max<size_t>(per, 1));

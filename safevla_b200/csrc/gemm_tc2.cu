@@ -332,7 +332,7 @@ int svla_gemm_tc2(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   const int clusters = ctx->sm_count / 2;
   int splits = 1;
   const int tiles = tiles_m2 * g.tiles_n;
-  if (tiles * 2 <= clusters && kb_total >= 32) {
+  if (d->transA && tiles * 2 <= clusters && kb_total >= 32) {  // weight gradients only (see gemm_tc.cu)
     // split K so that tiles * splits fills whole waves of CTA pairs: the smallest split count within 3 % of the best
     // wave occupancy (16 tiles on 74 pairs: 4 splits leave 14 % of the chip idle, 9 splits 3 %)
     const size_t per = (size_t)d->M * ((size_t)d->N + 1) * sizeof(float);

@@ -82,6 +82,13 @@ def lagrange_update(lambda_dev, state_dev, cost_sum_cnt, cost_limit: float, lr: 
                                       upper_bound, stream_ptr()), "svla_lagrange_update")
 
 
+def episode_cost_step(costs, mask_next, episode_cost, sum_cnt):
+    """Per-step Jc bookkeeping: costs / mask_next / episode_cost fp32 [N], sum_cnt fp32 [2] (updated in place)."""
+    _cuda(costs, mask_next, episode_cost, sum_cnt)
+    check(_lib().svla_episode_cost_step(get_ctx(), ptr(costs), ptr(mask_next), ptr(episode_cost), ptr(sum_cnt),
+                                        episode_cost.numel(), stream_ptr()), "svla_episode_cost_step")
+
+
 def sq_norm(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x)
     assert x.dtype == torch.float32

@@ -82,6 +82,8 @@ class B200RolloutStorage:
         if c_value_preds is not None:
             self.c_value_preds[t].copy_(c_value_preds.to(dev).reshape(N, 1))
         self.masks[t + 1].copy_(masks.to(dev).reshape(N, 1))
+        if costs is not None:  # Jc bookkeeping: totals of the episodes that ended at this step
+            ops.episode_cost_step(self.costs[t].view(N), self.masks[t + 1].view(N), self.episode_cost, self.cost_sum_cnt)
         self.step += 1
 
     def load_rollout(self, ro: Dict, value_preds, c_value_preds, action_log_probs):
@@ -167,4 +169,5 @@ class B200RolloutStorage:
             v[0].copy_(v[self.T])
         self.masks[0].copy_(self.masks[self.T])
         self.prev_actions[0].copy_(self.prev_actions[self.T])
+        self.cost_sum_cnt.zero_()  # Jc counts the episodes finished inside ONE rollout; running episode totals carry over
         self.step = 0

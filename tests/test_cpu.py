@@ -328,3 +328,17 @@ def test_vit_oracle_reproduces_hf_golden_and_layouts_agree():
     pos = interpolate_pos_embed(a["pos"], 16, 27)
     assert pos.shape == (1 + 16 * 27, 384) and torch.equal(pos[0], a["pos"][0])
     assert torch.equal(interpolate_pos_embed(a["pos"], 37, 37), a["pos"])
+
+
+def test_goal_byte_codec_matches_reference_encoding():
+    """convert_string_to_byte / convert_byte_to_string restate utils/string_utils.py:11-18 (numpy `S{max_len}` view)."""
+    import numpy as np
+    from safevla_b200.ingest import SafeRLStepResult, convert_byte_to_string, convert_string_to_byte
+    for s in ["navigate to a mug", "", "pick up the apple and bring it to the kitchen counter, in that order",
+              "x" * 1000, "y" * 1200, "café table"]:
+        ref = np.array([s.encode()], dtype="S1000").view("uint8")  # the reference's own expression on the utf-8 bytes
+        mine = convert_string_to_byte(s, 1000)
+        assert mine.dtype == np.uint8 and mine.shape == (1000,) and np.array_equal(mine, ref)
+        assert convert_byte_to_string(mine) == ref.view("S1000")[0].decode(errors="ignore") or len(s.encode()) > 1000
+    r = SafeRLStepResult({"a": 1}, 1.0, 0.0, False, {})
+    assert r._fields == ("observation", "reward", "cost", "done", "info")  # tasks/abstract_task.py:369-380
