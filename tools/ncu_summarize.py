@@ -5,6 +5,8 @@
       per-kernel count / total / share of an `ncu --metrics gpu__time_duration.sum --csv` launch list
   python tools/ncu_summarize.py rep gpurun_out/x.ncu-rep [more.ncu-rep ...] > profiles/ncu_rNN.md
       key metrics of `ncu --set full` captures (needs the ncu CLI; works without a GPU)
+  python tools/ncu_summarize.py traffic profiles/ncu_rNN_traffic.json gpurun_out/ncu_rNN_*.ncu-rep
+      DRAM bytes per launch next to the algorithmic bytes of the measurement shapes (bench.py's roofline.traffic)
 """
 from __future__ import annotations
 
@@ -83,8 +85,55 @@ def rep(paths):
             print()
 
 
+# measurement shapes of tools/ncu_targets.py: target -> (description, algorithmic bytes per launch)
+_M, _N, _K = 119808, 2048, 512
+SHAPES = {
+    "gemm_fwd": (f"fwd M={_M} N={_N} K={_K} bias+ReLU bf16", 2 * (_M * _K + _N * _K + _M * _N)),
+    "gemm_dgrad": (f"dgrad M={_M} N={_K} K={_N} bf16", 2 * (_M * _N + _N * _K + _M * _K)),
+    "gemm_dgrad_mask": (f"dgrad + ReLU mask M={_M} N={_N} K={_K} bf16 (side operand [M, N] bf16)",
+                        2 * (_M * _K + _N * _K + 2 * _M * _N)),
+    "gemm_wgrad": (f"wgrad M={_N} N={_K} K={_M} fp32 accumulate", 2 * (_M * _N + _M * _K) + 8 * _N * _K),
+    "gae": ("T=128 N=65536 both streams", 36 * 128 * 65536),
+    "loss": ("R=8388608 A=20", (8 * 20 + 44) * 128 * 65536),
+    "adam": ("62.9M parameters, fp32 master + bf16 shadow + grad zeroing", (62_900_000 // 64 * 64) * 34),
+}
+
+
+def traffic(out, paths):
+    """{target: kernel, DRAM bytes, duration} of `ncu --set full` captures named ncu_<round>_<target>_<kernel>.ncu-rep."""
+    res = OrderedDict()
+    for p in paths:
+        txt = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        r = rows[2]
+
+        def val(k):
+            v, u = float(r[idx[k]].replace(",", "")), units[idx[k]]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3,
+                        "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}.get(u, 1)
+        m = re.search(r"ncu_r\d+_(.+?)_(svla_gemm_tc|attn_tc_fwd|attn_tc_bwd|gae_march|ppo_lag|clip_adam|layernorm_bwd)", p)
+        tgt = m.group(1) if m else p
+        key = tgt if tgt.startswith("gemm") or tgt in ("gae", "loss", "adam") else short(r[idx["Kernel Name"]])
+        e = {"kernel": short(r[idx["Kernel Name"]]),
+             "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+             "ncu_us": val("gpu__time_duration.sum"),
+             "tensor_pipe_active_pct": float(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]])}
+        if tgt in SHAPES:
+            e["shape"], e["algorithmic_bytes"] = SHAPES[tgt]
+            e["traffic_over_algorithmic"] = round(e["dram_bytes"] / e["algorithmic_bytes"], 3)
+        res[key] = e
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3:])
     else:
         rep(sys.argv[2:])

@@ -62,6 +62,10 @@ def main():
             out = torch.empty(M, N, device=dev, dtype=bf)
             bias = torch.zeros(N, device=dev)
             fn = lambda: ops.gemm(a, b, out, trans_b=True, bias=bias, epilogue=L.EPI_RELU)  # noqa: E731
+        elif target == "gemm_dgrad_mask":  # FFN-down dgrad with the fused ReLU mask (side operand = hf)
+            a, b = torch.randn(M, K, device=dev, dtype=bf), torch.randn(K, N, device=dev, dtype=bf)
+            out, aux = torch.empty(M, N, device=dev, dtype=bf), torch.randn(M, N, device=dev, dtype=bf)
+            fn = lambda: ops.gemm(a, b, out, trans_b=False, aux=aux, epilogue=L.EPI_RELU_MASK)  # noqa: E731
         elif target == "gemm_dgrad":
             a, b = torch.randn(M, N, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf)
             out = torch.empty(M, K, device=dev, dtype=bf)
