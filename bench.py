@@ -98,9 +98,10 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int):
-    """Times the CPU oracle's whole update on a sampler-subsample (sample_N of the N samplers, first sample_T
-    steps, ONE update repeat); returns samples/s and a description."""
+def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int, device: str = "cpu"):
+    """Times the oracle's whole update on a sampler-subsample (sample_N of the N samplers, first sample_T steps, ONE
+    update repeat); returns samples/s and a description.  device="cuda" runs the same torch-eager restatement on the
+    GPU (fp32, TF32 off): the stock-library baseline of SURVEY 8d, reported in DESIGN.md, never by the driver's arms."""
     from oracle.update_oracle import oracle_update  # the one place bench.py executes oracle/
     from safevla_b200.params import init_state_dict
     from safevla_b200.synthetic import RolloutSpec, make_rollout
@@ -114,24 +115,44 @@ def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int):
     cvp = torch.randn(sample_T + 1, sample_N, 1, generator=g).abs()
     logp = -3.0 + 0.05 * torch.randn(sample_T, sample_N, generator=g)
     cfg = PPOLagConfig(update_repeats=1)
+    if device != "cpu":
+        def mv(x):
+            if isinstance(x, dict):
+                return {k: mv(v) for k, v in x.items()}
+            return x.to(device) if torch.is_tensor(x) else x
+        sd, ro, vp, cvp, logp = mv(sd), mv(ro), vp.to(device), cvp.to(device), logp.to(device)
+        torch.set_default_device(device)  # the restatement creates its index / mask tensors with bare factories
     times = []
     for i in range(warmup + steps):
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         oracle_update(sd, ro, vp, cvp, logp, cfg, wl["A"], wl["C"])
+        if device != "cpu":
+            torch.cuda.synchronize()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
-    return sample_T * sample_N / t, t, (f"CPU oracle (torch eager fp32, {torch.get_num_threads()} threads): "
-                                        f"{sample_N} of {wl['N']} samplers x {sample_T} of {wl['T']} steps, 1 of "
-                                        f"{UPDATE_REPEATS} update repeats per step")
+    what = (f"CPU oracle (torch eager fp32, {torch.get_num_threads()} threads)" if device == "cpu"
+            else "torch-eager oracle on the GPU (fp32)")
+    return sample_T * sample_N / t, t, (f"{what}: {sample_N} of {wl['N']} samplers x {sample_T} of {wl['T']} steps, "
+                                        f"1 of {UPDATE_REPEATS} update repeats per step")
 
 
 def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=min(wl["T"], 32), sample_N=1)
-    line = {"impl": "reference", "metric": "ppo_lagrangian_update_samples_per_sec", "value": v, "unit": "samples/s",
+    if args.ref_device != "cpu":  # stock-library baseline on the GPU: larger sample, same code
+        if args.ref_tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+        v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=wl["T"], sample_N=min(wl["N"], args.ref_samplers),
+                                device=args.ref_device)
+        desc += " (TF32 matmuls)" if args.ref_tf32 else ""
+    else:
+        v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=min(wl["T"], 32), sample_N=1)
+    line = {"impl": "reference" if args.ref_device == "cpu" else "reference-eager-" + args.ref_device, "metric": "ppo_lagrangian_update_samples_per_sec", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "T": wl["T"], "N_global": wl["N"], "actions": wl["A"], "cameras": wl["C"],
@@ -348,6 +369,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", help="--impl reference only: cpu (the reference arm) or cuda")
+    ap.add_argument("--ref-samplers", type=int, default=2, help="--ref-device cuda: samplers in the timed sample")
+    ap.add_argument("--ref-tf32", action="store_true", help="--ref-device cuda: allow TF32 tensor-core matmuls")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

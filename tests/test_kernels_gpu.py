@@ -545,6 +545,53 @@ def test_gemm_tcgen05(dev, M, N, K, ta, tb):
     assert (acc.double() - exp2).abs().max().item() < 2e-5 * max(scale, 1.0) * max(1.0, (K / 512) ** 0.5)
 
 
+@pytest.mark.parametrize("M,N,K,tb", [(117 * 70, 1024, 512, True), (117 * 70, 512, 512, False), (1000, 256, 192, True),
+                                      (130, 128, 64, True), (40000, 512, 128, False)])
+def test_gemm_tcgen05_epilogue_combinations(dev, M, N, K, tb):
+    """Every compile-time specialised epilogue (tc_common.cuh: epilogue kind x bias x residual x accumulate, bf16 and
+    fp32 outputs) and the run-time generic one, on shapes with many tiles per CTA (side-operand prefetch across tile
+    boundaries), ragged M and both kernels (pair / single CTA)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev, torch.bfloat16)
+    B = (torch.randn((N, K) if tb else (K, N), generator=g) * 0.5).to(dev, torch.bfloat16)
+    ref = A.double() @ (B.t() if tb else B).double()
+    scale = ref.abs().max().item()
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+    aux = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)
+    aux[::7] = 0.0  # exact zeros and negative zeros must mask like ReLU'(0) = 0
+    aux[3::11] = -0.0
+    E = _L()
+    gelu = lambda x: 0.5 * x * (1.0 + torch.erf(x / 2 ** 0.5))  # noqa: E731
+    cases = [  # (epilogue, bias, residual, alpha) -> expected
+        (E.EPI_NONE, True, False, 1.0, ref + bias.double()),
+        (E.EPI_RELU, True, False, 1.0, torch.relu(ref + bias.double())),
+        (E.EPI_NONE, True, True, 1.0, ref + bias.double() + res.double()),
+        (E.EPI_RELU_MASK, False, False, 1.0, ref * (aux.double() > 0)),
+        (E.EPI_NONE, False, True, 1.0, ref + res.double()),
+        (E.EPI_NONE, False, False, 1.0, ref),
+        (E.EPI_GELU, True, False, 1.0, gelu(ref + bias.double())),
+        (E.EPI_RELU_MASK, False, True, 1.0, ref * (aux.double() > 0) + res.double()),   # generic path
+        (E.EPI_RELU, False, False, 0.5, torch.relu(0.5 * ref)),                         # generic path, alpha
+    ]
+    for epi, use_b, use_r, alpha, exp in cases:
+        out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+        _ops().gemm(A, B, out, trans_b=tb, bias=bias if use_b else None, residual=res if use_r else None,
+                    aux=aux if epi == E.EPI_RELU_MASK else None, epilogue=epi, alpha=alpha, impl=2)
+        err = (out.double() - exp).abs().max().item()
+        assert err < 1e-2 * max(scale, 1.0), (epi, use_b, use_r, err)
+        if epi == E.EPI_RELU_MASK and not use_r:
+            assert (out[aux <= 0] == 0).all(), "masked entries must be exact zeros"
+    # fp32 outputs: plain, + fp32 residual, accumulate
+    res32 = torch.randn(M, N, generator=g).to(dev)
+    for use_r, acc in ((False, False), (True, False), (False, True)):
+        out = torch.randn(M, N, generator=g).to(dev)
+        out0 = out.clone()
+        _ops().gemm(A, B, out, trans_b=tb, residual=res32 if use_r else None, accumulate=acc, impl=2)
+        exp = ref + (res32.double() if use_r else 0) + (out0.double() if acc else 0)
+        assert (out.double() - exp).abs().max().item() < 2e-5 * max(scale, 1.0) * max(1.0, (K / 512) ** 0.5)
+
+
 @pytest.mark.parametrize("M,N,K", [(512, 512, 117 * 256), (2048, 512, 117 * 64), (1536, 512, 4000), (256, 256, 64),
                                    (512, 384, 84 * 96), (300, 512, 1000), (128, 512, 2048), (20, 512, 8192)])
 def test_gemm_wgrad_fused_bias_gradient(dev, M, N, K):
