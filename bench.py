@@ -38,7 +38,8 @@ WORKLOADS = {
     "cfg1_1env_16step": dict(T=16, N=1, A=6, C=1, L=32, gflop_per_sample=18.4),
     # configs[3] PickupType head, two cameras (S = 201)
     "cfg4_32env_256step": dict(T=256, N=32, A=20, C=2, L=32, gflop_per_sample=31.5),
-    "cfg5_128env_128step": dict(T=128, N=128, A=20, C=2, L=32, gflop_per_sample=31.5),
+    # configs[4]: FetchType multi-task, dual cost channels (K = 2: extension beyond the reference's scalar cost)
+    "cfg5_128env_128step": dict(T=128, N=128, A=20, C=2, L=32, K=2, gflop_per_sample=31.5),
 }
 UPDATE_REPEATS = 4
 
@@ -233,26 +234,41 @@ def run_b200(args, wl, name):
     # GAE / fused-loss roofline shapes first: each kernel timed alone (burst conditions, like the copy that
     # MEASURED_PEAKS.json's HBM figure comes from), not after seconds of power-capped tensor-core work
     scan = scan_roofline(dev, pk) if world == 1 else None
+    K = wl.get("K", 1)  # cost channels
     model = B200SafeActorCritic(A, C, precision=args.precision, seed=0, device=dev, chunk_rows=args.chunk_rows,
-                                extras="off", verify_dedupe=False)
-    cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS)
+                                extras="off", verify_dedupe=False, num_cost_channels=K)
+    cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS, cost_limit=2.31964 if K == 1 else (2.31964,) * K)
     upd = PPOLagUpdater(model, cfg)
-    ro = make_rollout(RolloutSpec(T, n_local, A, C, prompt_tokens=wl["L"], seed=1234), rank=rank, pin=True)
-    storage = B200RolloutStorage(T, dev)
+    ro = make_rollout(RolloutSpec(T, n_local, A, C, prompt_tokens=wl["L"], seed=1234, num_cost_channels=K), rank=rank,
+                      pin=True)
+    storage = B200RolloutStorage(T, dev, num_cost_channels=K)
 
     # ---- "collection": value / cost-value predictions and old log-probs from the model's own forward
     obs_full = {k: v.to(dev) for k, v in ro["observations"].items()}
     pa_full = torch.cat([torch.zeros(1, n_local, dtype=torch.int64), ro["actions"]], 0).to(dev)
     mk_full = ro["masks"].to(dev).view(T + 1, n_local)
+    def collect(t0, t1):  # one update-mode forward of the three towers over steps [t0, t1)
+        model._ctx_cache = None
+        rc = model.prepare({k: v[t0:t1] for k, v in obs_full.items()}, t1 - t0, n_local)
+        return {i: model.tower_forward(i, rc, pa_full[t0:t1].contiguous(), mk_full[t0:t1].contiguous(), keep=False,
+                                       want_logits=(i == ACTOR), want_values=(i != ACTOR))[0]
+                for i in (ACTOR, CRITIC, COST)}
+
     with torch.no_grad():
-        rc = model.prepare(obs_full, T + 1, n_local)
-        outs = {i: model.tower_forward(i, rc, pa_full, mk_full, keep=False, want_logits=(i == ACTOR),
-                                       want_values=(i != ACTOR))[0] for i in (ACTOR, CRITIC, COST)}
-        logp = torch.log_softmax(outs[ACTOR]["logits"][:T], -1).gather(-1, ro["actions"].to(dev).unsqueeze(-1))
-    vp_host = outs[CRITIC]["values"].cpu().pin_memory()
-    cvp_host = outs[COST]["values"].cpu().pin_memory()
+        if T + 1 <= 256:
+            outs = collect(0, T + 1)
+            vals, cvals, logits = outs[CRITIC]["values"], outs[COST]["values"], outs[ACTOR]["logits"][:T]
+        else:  # the decoder's window is 256 steps (config 4: T = 256): bootstrap row from the window shifted by one
+            outs, last = collect(0, T), collect(1, T + 1)
+            vals = torch.cat([outs[CRITIC]["values"], last[CRITIC]["values"][-1:]], 0)
+            cvals = torch.cat([outs[COST]["values"], last[COST]["values"][-1:]], 0)
+            logits = outs[ACTOR]["logits"]
+            del last
+        logp = torch.log_softmax(logits, -1).gather(-1, ro["actions"].to(dev).unsqueeze(-1))
+    vp_host = vals.cpu().pin_memory()
+    cvp_host = cvals.cpu().pin_memory()
     logp_host = logp.squeeze(-1).cpu().pin_memory()
-    del obs_full, outs, rc
+    del obs_full, outs, vals, cvals, logits
     model._ctx_cache = None
     storage.load_rollout(ro, vp_host, cvp_host, logp_host)
     torch.cuda.synchronize()
@@ -266,14 +282,14 @@ def run_b200(args, wl, name):
         model._ctx_cache = None  # a new rollout every step: rebuild the observation-derived caches
         return upd.update(storage)
 
-    host_out = torch.empty(18, pin_memory=True)
+    host_out = torch.empty(16 + 8, pin_memory=True)
 
     def step_e2e():
         model._ctx_cache = None
         storage.load_rollout(ro, vp_host, cvp_host, logp_host)  # pinned host -> HBM
         res = upd.update(storage)
         host_out[:16].copy_(res["loss_scalars"], non_blocking=True)
-        host_out[16:17].copy_(res["lambda"], non_blocking=True)
+        host_out[16:16 + K].copy_(res["lambda"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return res
 
@@ -336,11 +352,12 @@ def run_b200(args, wl, name):
         "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": name, "T": T, "N_global": wl["N"], "N_per_rank": n_local, "actions": A, "cameras": C,
-                   "prompt_tokens": wl["L"], "update_repeats": UPDATE_REPEATS, "parallelism": f"dp{world}",
+                   "prompt_tokens": wl["L"], "cost_channels": K, "update_repeats": UPDATE_REPEATS,
+                   "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (1.06 GB of observations per rank-rollout at N=64)",
                    "precision": args.precision, "chunk_rows": args.chunk_rows},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": storage.h2d_bytes(),
-                "d2h_bytes_per_step": 17 * 4, "ms_per_step": t_e2e * 1e3},
+                "d2h_bytes_per_step": (16 + K) * 4, "ms_per_step": t_e2e * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

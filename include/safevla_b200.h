@@ -300,6 +300,15 @@ int svla_hash_rows(svla_ctx* ctx, const uint8_t* rows, long long R, int L, uint6
 int svla_episode_cost_step(svla_ctx* ctx, const float* costs, const float* mask_next, float* episode_cost,
                            float* sum_cnt, int N, svla_stream stream);
 
+/* K cost channels (extension: the reference has one scalar cost, tasks/abstract_task.py:333; BASELINE config 5 asks
+ * for two).  The constraint term of SafePPOLogGrad (customized_loss.py:350-359) generalises to
+ *   (A - sum_k lambda_k A_c,k) / (1 + sum_k lambda_k),
+ * which equals the single-channel form with lambda_eff = sum_k lambda_k and c_adv_eff = sum_k lambda_k A_c,k /
+ * lambda_eff (0 when lambda_eff = 0): this entry point produces that pair on the device (multipliers are read on the
+ * device) so svla_ppo_lag_fwd_bwd is used unchanged.  c_adv: channel-major [K, R] fp32, 1 <= K <= 8. */
+int svla_combine_cost_advantages(svla_ctx* ctx, const float* c_adv, const float* lambdas_dev, int K, long long R,
+                                 float* c_adv_eff, float* lambda_eff_dev, svla_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,12 +21,20 @@ def oracle_update(sd: Dict[str, torch.Tensor], ro: Dict, value_preds, c_value_pr
     prev = torch.cat([torch.zeros_like(ro["actions"][:1]), ro["actions"][:-1]], 0)
     masks = ro["masks"][:T]
     ret, adv = TO.gae_returns(ro["rewards"], value_preds, ro["masks"], cfg.gamma, cfg.gae_lambda)
-    cret, cadv = TO.gae_returns(ro["costs"], c_value_preds, ro["masks"], cfg.gamma, cfg.gae_lambda)
+    # K cost channels (K = 1: the reference; K > 1: the extension of DESIGN.md section 8): one GAE per channel
+    K = ro["costs"].shape[-1]
+    c_value_preds = c_value_preds.reshape(T + 1, -1, K)
+    chan = [TO.gae_returns(ro["costs"][..., k:k + 1], c_value_preds[..., k:k + 1], ro["masks"], cfg.gamma,
+                           cfg.gae_lambda) for k in range(K)]
+    cret, cadv = chan[0]
+    limits = list(cfg.cost_limit) if isinstance(cfg.cost_limit, (list, tuple)) else [cfg.cost_limit]
+    assert len(limits) == K
     params = {k: v.clone() for k, v in sd.items()}
     trainable = [k for k in params if "text_encoder" not in k and not k.endswith("div_term")]
     m = {k: torch.zeros_like(params[k]) for k in trainable}
     v = {k: torch.zeros_like(params[k]) for k in trainable}
-    lag = TO.LagrangeOracle(cfg.cost_limit, cfg.lambda_init, cfg.lambda_lr, cfg.lambda_upper_bound)
+    lags = [TO.LagrangeOracle(l, cfg.lambda_init, cfg.lambda_lr, cfg.lambda_upper_bound) for l in limits]
+    lag = lags[0]
     info = {}
     # the frozen T5 does not change inside an update: evaluate it once (identical result)
     ids, am = TO.decode_goal_ids(obs["natural_language_spec"].reshape(T * masks.shape[1], -1))
@@ -39,13 +47,20 @@ def oracle_update(sd: Dict[str, torch.Tensor], ro: Dict, value_preds, c_value_pr
             outs[pre] = TO.tower_forward(leaf, pre, obs, th, prev, masks, num_actions, num_cameras)
         logits, values, c_values = outs[""][0], outs["critic_tsfm."][1], outs["c_critic_tsfm."][1]
         if cfg.stage == 0:
-            total = TO.ppo_value_loss(values, ret[:T]) + TO.ppo_value_loss(c_values, cret[:T])
+            total = TO.ppo_value_loss(values, ret[:T])
+            for k in range(K):  # sum over channels of the per-channel SafePPOValue means
+                total = total + TO.ppo_value_loss(c_values[..., k:k + 1], chan[k][0][:T])
         else:
-            total, _ = TO.safe_ppo_log_grad(logits, ro["actions"], old_logp, adv, cadv, values, ret[:T], lag.lam,
+            lam_sum = sum(l.lam for l in lags)
+            cadv_eff = cadv if K == 1 else (sum(l.lam * chan[k][1] for k, l in enumerate(lags)) / lam_sum
+                                            if lam_sum > 0 else torch.zeros_like(cadv))
+            # (A - sum_k lam_k A_c,k) / (1 + sum_k lam_k)
+            total, _ = TO.safe_ppo_log_grad(logits, ro["actions"], old_logp, adv, cadv_eff, values, ret[:T],
+                                            lag.lam if K == 1 else lam_sum,
                                             clip_param=cfg.clip_param, value_loss_coef=cfg.value_loss_coef,
                                             entropy_coef=cfg.entropy_coef)
         total.backward()
-        info["last_total"] = float(total)
+        info["last_total"] = float(total.detach())
         with_grad = [k for k in trainable if leaf[k].grad is not None]
         grads, norm = TO.clip_grad_norm([leaf[k].grad for k in with_grad], cfg.max_grad_norm)
         info["grad_norm"] = float(norm)
@@ -53,6 +68,7 @@ def oracle_update(sd: Dict[str, torch.Tensor], ro: Dict, value_preds, c_value_pr
         for k, g in zip(with_grad, grads):
             params[k], m[k], v[k] = TO.adam_step(params[k], g, m[k], v[k], step, cfg.lr, cfg.betas[0], cfg.betas[1],
                                                  cfg.eps)
-    jc = float(ro["episode_cost_sum"]) / max(float(ro["episode_count"]), 1.0)
-    lam = lag.update(jc)
-    return params, lam, info
+    cnt = max(float(ro["episode_count"]), 1.0)
+    sums = ro["episode_cost_sum"].reshape(-1).tolist()
+    lams = [l.update(sums[k] / cnt) for k, l in enumerate(lags)]
+    return params, (lams[0] if K == 1 else lams), info

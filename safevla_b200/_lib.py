@@ -106,6 +106,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_cast_bf16": [c_p, c_p, c_p, c_ll, c_p],
     "svla_hash_rows": [c_p, c_p, c_ll, C.c_int, c_p, c_p],
     "svla_episode_cost_step": [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p],
+    "svla_combine_cost_advantages": [c_p, c_p, c_p, C.c_int, c_ll, c_p, c_p, c_p],
 }
 _RESTYPES = {"svla_last_error": C.c_char_p, "svla_launch_count": C.c_ulonglong}
 

@@ -469,3 +469,51 @@ extern "C" int svla_episode_cost_step(svla_ctx* ctx, const float* costs, const f
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
+
+
+// ---- K cost channels: fold the per-channel cost advantages and multipliers into the single pair the fused loss takes
+//   (A - sum_k lambda_k A_c,k) / (1 + sum_k lambda_k)  ==  (A - L * A_eff) / (1 + L),  L = sum_k lambda_k,
+//   A_eff = sum_k lambda_k A_c,k / L   (A_eff = 0 when L = 0).   c_adv is channel-major [K, R]; 16-byte accesses.
+__global__ void __launch_bounds__(256) combine_cost_adv_kernel(const float* __restrict__ c_adv,
+                                                               const float* __restrict__ lambdas, int K, long long R,
+                                                               float* __restrict__ out, float* __restrict__ lambda_eff) {
+  float lam[8];
+  float L = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    lam[k] = k < K ? lambdas[k] : 0.f;
+    L += lam[k];
+  }
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) lambda_eff[0] = L;
+  const long long R4 = R >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(c_adv + (long long)k * R) + i);
+      acc.x = fmaf(lam[k], v.x, acc.x); acc.y = fmaf(lam[k], v.y, acc.y);
+      acc.z = fmaf(lam[k], v.z, acc.z); acc.w = fmaf(lam[k], v.w, acc.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+  if (blockIdx.x == 0) {  // tail (R % 4 rows)
+    for (long long i = (R4 << 2) + threadIdx.x; i < R; i += blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc = fmaf(lam[k], c_adv[(long long)k * R + i], acc);
+      out[i] = acc * inv;
+    }
+  }
+}
+
+extern "C" int svla_combine_cost_advantages(svla_ctx* ctx, const float* c_adv, const float* lambdas_dev, int K,
+                                            long long R, float* c_adv_eff, float* lambda_eff_dev, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && c_adv && lambdas_dev && c_adv_eff && lambda_eff_dev, "NULL argument");
+  SVLA_CHECK_ARG(K >= 1 && K <= 8, "1 <= K <= 8 cost channels");
+  if (R <= 0) return SVLA_OK;
+  // channel k starts at c_adv + k * R: 16-byte aligned vector loads need R % 4 == 0 for k > 0
+  SVLA_CHECK_ARG(K == 1 || R % 4 == 0, "R must be a multiple of 4 for K > 1 (16-byte channel alignment)");
+  const int grid = (int)std::min<long long>((R / 4 + 255) / 256 + 1, (long long)ctx->sm_count * 8);
+  combine_cost_adv_kernel<<<grid, 256, 0, as_stream(stream)>>>(c_adv, lambdas_dev, K, R, c_adv_eff, lambda_eff_dev);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}

@@ -47,8 +47,8 @@ def _flat(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 def _lambda_dev(lm, device) -> torch.Tensor:
     if not torch.is_tensor(lm):
-        lm = torch.tensor(float(lm))
-    return lm.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+        lm = torch.tensor(lm, dtype=torch.float32)
+    return lm.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()  # [1], or [K] cost channels
 
 
 def fused_ppo_loss(*, logits, values, c_values, batch, hp: L.PpoHparams, lagrangian_multiplier=None,
@@ -57,11 +57,15 @@ def fused_ppo_loss(*, logits, values, c_values, batch, hp: L.PpoHparams, lagrang
     lam = _lambda_dev(lagrangian_multiplier, dev) if lagrangian_multiplier is not None else None
     g = lambda k: _flat(batch[k].to(dev)) if (k in batch and batch[k] is not None) else None  # noqa: E731
     actions = g("actions") if logits is not None else None
+    c_adv = g(c_adv_key) if (logits is not None and hp.use_lagrangian) else None
+    if lam is not None and lam.numel() > 1 and c_adv is not None:
+        # K cost channels (extension): c_adv is channel-major [K, T, N, 1]; fold (A_c,k, lambda_k) into one pair
+        c_adv, lam = ops.combine_cost_advantages(c_adv.view(lam.numel(), -1), lam)
     scal, dlogits, dvalues, dcvalues = ops.ppo_lag_fwd_bwd(
         _flat(logits.detach()) if logits is not None else None, actions,
         g("old_action_log_probs") if logits is not None else None,
         g(adv_key) if logits is not None else None,
-        g(c_adv_key) if (logits is not None and hp.use_lagrangian) else None,
+        c_adv,
         _flat(values.detach()) if values is not None else None, g("returns") if values is not None else None,
         _flat(c_values.detach()) if c_values is not None else None,
         g(c_returns_key) if c_values is not None else None, lam, hp,

@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import ops
 from .misc import CategoricalDistr, Memory, SafeActorCriticOutput
-from .params import D, TOWERS, ParamLayout, T5Layout, init_state_dict, t5_spec, tower_spec
+from .params import D, TOWERS, ParamLayout, T5Layout, init_state_dict, t5_spec, tower_spec, tower_values
 from .tower import TOK, EncStash, T5Encoder, Tower, TowerWeights
 
 ACTOR, CRITIC, COST = 0, 1, 2
@@ -92,13 +92,16 @@ class B200SafeActorCritic(nn.Module):
                  goal_sensor_uuid: str = "natural_language_spec", rgb_uuid: str = "rgb_dinov2",
                  manip_uuid: str = "manipulation_rgb_dinov2", in_hand_uuid: str = "an_object_is_in_hand",
                  time_step_uuid: str = "time_step", traj_idx_uuid: str = "traj_index", extras: str = "eager",
-                 verify_dedupe: bool = True, max_steps: int = 1000):
+                 verify_dedupe: bool = True, max_steps: int = 1000, num_cost_channels: int = 1):
         super().__init__()
         assert precision in ("bf16", "fp32")
         if not torch.cuda.is_available():
             raise RuntimeError("B200SafeActorCritic needs a CUDA device (sm_100a); there is no CPU fallback")
         self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.A, self.C = num_actions, num_cameras
+        # K cost channels (extension beyond the reference's single scalar cost, tasks/abstract_task.py:333): the cost
+        # critic's head predicts K values; K = 1 is the reference model, key for key
+        self.K = int(num_cost_channels)
         self.precision = precision
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.uu = dict(goal=goal_sensor_uuid, rgb=rgb_uuid, manip=manip_uuid, hand=in_hand_uuid,
@@ -108,7 +111,7 @@ class B200SafeActorCritic(nn.Module):
         self.extras_mode, self.verify_dedupe = extras, verify_dedupe
         self.trainable_towers: Tuple[int, ...] = (ACTOR, CRITIC, COST)
 
-        self.layout, self.t5_layout = ParamLayout(num_actions, num_cameras), T5Layout()
+        self.layout, self.t5_layout = ParamLayout(num_actions, num_cameras, self.K), T5Layout()
         f32 = dict(device=self.dev, dtype=torch.float32)
         self.param_arena = torch.zeros(self.layout.total, **f32)
         self.grad_arena = torch.zeros(self.layout.total, **f32)
@@ -117,7 +120,7 @@ class B200SafeActorCritic(nn.Module):
         self.t5_arena = torch.zeros(self.t5_layout.total, **f32)
         self._register_names()
         self.load_state_dict(state_dict if state_dict is not None
-                             else init_state_dict(num_actions, num_cameras, seed), strict=True)
+                             else init_state_dict(num_actions, num_cameras, seed, num_cost_channels=self.K), strict=True)
 
         self.t5 = T5Encoder(self.t5_layout, self.t5_arena, self.adt)
         self.towers: List[Tower] = []
@@ -146,8 +149,8 @@ class B200SafeActorCritic(nn.Module):
         return m
 
     def _register_names(self):
-        for pre in TOWERS:
-            for k, shape, _ in tower_spec(self.A, self.C):
+        for ti, pre in enumerate(TOWERS):
+            for k, shape, _ in tower_spec(self.A, self.C, tower_values(ti, self.K)):
                 name = pre + k
                 parts = name.split(".")
                 p = nn.Parameter(self.layout.view(self.param_arena, name), requires_grad=True)
@@ -396,9 +399,9 @@ class B200SafeActorCritic(nn.Module):
         buf = torch.empty(4, device=self.dev)
         ops.sq_norm(self.grad_arena[lo:hi], buf[0:1])
         wslot, bslot = self.layout.slots[pre + "critic.fc.weight"], self.layout.slots[pre + "critic.fc.bias"]
-        ops.sq_norm(self.param_arena[wslot.offset: wslot.offset + 512], buf[1:2])
+        ops.sq_norm(self.param_arena[wslot.offset: wslot.offset + wslot.numel], buf[1:2])
         ops.sq_norm(self.param_arena[bslot.offset: bslot.offset + 4], buf[2:3])  # padded slot: zeros beyond [1]
-        ops.sq_norm(self.grad_arena[wslot.offset: wslot.offset + 512], buf[3:4])
+        ops.sq_norm(self.grad_arena[wslot.offset: wslot.offset + wslot.numel], buf[3:4])
         host = buf.cpu().sqrt()
         return {"total_norm": host[0:1].clone(), "weight_norm": host[1:2].clone(), "bias_norm": host[2:3].clone(),
                 "weight_grad_norm": host[3:4].clone(), "stop_grad_values": c_values.detach()}

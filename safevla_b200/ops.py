@@ -89,6 +89,19 @@ def episode_cost_step(costs, mask_next, episode_cost, sum_cnt):
                                         episode_cost.numel(), stream_ptr()), "svla_episode_cost_step")
 
 
+def combine_cost_advantages(c_adv: torch.Tensor, lambdas: torch.Tensor):
+    """c_adv fp32 [K, ...] (channel-major), lambdas fp32 [K] (device) -> (c_adv_eff [...], lambda_eff [1]) such that
+    (A - sum_k l_k A_k) / (1 + sum_k l_k) == (A - l_eff A_eff) / (1 + l_eff)."""
+    _cuda(c_adv, lambdas)
+    K = c_adv.shape[0]
+    assert lambdas.numel() == K and c_adv.dtype == torch.float32 and lambdas.dtype == torch.float32
+    out = torch.empty(c_adv.shape[1:], device=c_adv.device, dtype=torch.float32)
+    lam = torch.empty(1, device=c_adv.device, dtype=torch.float32)
+    check(_lib().svla_combine_cost_advantages(get_ctx(), ptr(c_adv), ptr(lambdas), K, out.numel(), ptr(out), ptr(lam),
+                                              stream_ptr()), "svla_combine_cost_advantages")
+    return out, lam
+
+
 def sq_norm(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x)
     assert x.dtype == torch.float32

@@ -30,10 +30,11 @@ def allreduce_arena(comm: torch.Tensor, n_grad: int, cost_sum_cnt: Optional[torc
     buffer over the ranks in place and returns the factor that turns the summed gradients into the global-batch
     mean (equal shards: 1 / world)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    if cost_sum_cnt is not None:
-        comm[n_grad:n_grad + 2].copy_(cost_sum_cnt)
+    if cost_sum_cnt is not None:  # 2 floats per cost channel
+        assert cost_sum_cnt.numel() <= TAIL
+        comm[n_grad:n_grad + cost_sum_cnt.numel()].copy_(cost_sum_cnt)
     else:
-        comm[n_grad:n_grad + 2].zero_()
+        comm[n_grad:n_grad + TAIL].zero_()
     if world > 1:
         dist.all_reduce(comm, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / world

@@ -24,8 +24,9 @@ T5_VOCAB = 32128
 ALIGN = 64  # elements; keeps every tensor 256 B (fp32) / 128 B (bf16) aligned for TMA
 
 
-def tower_spec(num_actions: int, num_cameras: int) -> List[Tuple[str, Tuple[int, ...], str]]:
-    """(name, shape, init) for the trainable tensors of ONE tower, in reference state_dict order."""
+def tower_spec(num_actions: int, num_cameras: int, num_values: int = 1) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(name, shape, init) for the trainable tensors of ONE tower, in reference state_dict order.  `num_values` is the
+    width of the critic head: 1 in the reference; K for the cost tower of the K-cost-channel extension."""
     ve = "visual_encoder."
     s: List[Tuple[str, Tuple[int, ...], str]] = [
         (ve + "fusion_token", (D,), "token"),
@@ -84,8 +85,8 @@ def tower_spec(num_actions: int, num_cameras: int) -> List[Tuple[str, Tuple[int,
         ("decoder.output.weight", (D, D), "linear"),
         ("actor.linear.weight", (num_actions, D), "actor"),
         ("actor.linear.bias", (num_actions,), "zeros"),
-        ("critic.fc.weight", (1, D), "critic"),
-        ("critic.fc.bias", (1,), "zeros"),
+        ("critic.fc.weight", (num_values, D), "critic"),
+        ("critic.fc.bias", (num_values,), "zeros"),
     ]
     return s
 
@@ -141,16 +142,21 @@ def _init(shape, kind: str, g: torch.Generator, actor_gain: float) -> torch.Tens
     raise ValueError(kind)
 
 
-def init_state_dict(num_actions: int, num_cameras: int, seed: int, actor_gain: float = 0.01
-                    ) -> "OrderedDict[str, torch.Tensor]":
+def tower_values(tower_index: int, num_cost_channels: int) -> int:
+    """Critic-head width of tower `tower_index`: the cost critic (index 2) predicts one value per cost channel."""
+    return num_cost_channels if tower_index == 2 else 1
+
+
+def init_state_dict(num_actions: int, num_cameras: int, seed: int, actor_gain: float = 0.01,
+                    num_cost_channels: int = 1) -> "OrderedDict[str, torch.Tensor]":
     """Deterministic (CPU generator) random init with the reference's key set; the three towers
     get independent trainable weights and the SAME frozen T5 weights (as `from_pretrained` gives)."""
     g = torch.Generator().manual_seed(seed)
     t5 = OrderedDict((k, _init(shape, kind, g, actor_gain)) for k, shape, kind in t5_spec())
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     div_term = torch.exp(torch.arange(0, D, 2) * (-math.log(10000.0) / D))
-    for pre in TOWERS:
-        for k, shape, kind in tower_spec(num_actions, num_cameras):
+    for ti, pre in enumerate(TOWERS):
+        for k, shape, kind in tower_spec(num_actions, num_cameras, tower_values(ti, num_cost_channels)):
             sd[pre + k] = _init(shape, kind, g, actor_gain)
             if k == "last_actions_embed.weight":
                 sd[pre + k][num_actions + 1].zero_()  # padding_idx row
@@ -174,14 +180,14 @@ class Slot:
 class ParamLayout:
     """Offsets of every trainable tensor inside the flat arena (all three towers)."""
 
-    def __init__(self, num_actions: int, num_cameras: int):
-        self.num_actions, self.num_cameras = num_actions, num_cameras
+    def __init__(self, num_actions: int, num_cameras: int, num_cost_channels: int = 1):
+        self.num_actions, self.num_cameras, self.num_cost_channels = num_actions, num_cameras, num_cost_channels
         self.slots: "OrderedDict[str, Slot]" = OrderedDict()
         self.tower_range: Dict[str, Tuple[int, int]] = {}
         off = 0
-        for pre in TOWERS:
+        for ti, pre in enumerate(TOWERS):
             start = off
-            for k, shape, _ in tower_spec(num_actions, num_cameras):
+            for k, shape, _ in tower_spec(num_actions, num_cameras, tower_values(ti, num_cost_channels)):
                 n = int(torch.Size(shape).numel())
                 self.slots[pre + k] = Slot(pre + k, shape, off, n)
                 off += (n + ALIGN - 1) // ALIGN * ALIGN

@@ -19,10 +19,14 @@ from .misc import Memory
 
 
 class B200RolloutStorage:
-    def __init__(self, num_steps: int, device: Optional[torch.device] = None):
+    def __init__(self, num_steps: int, device: Optional[torch.device] = None, num_cost_channels: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("B200RolloutStorage keeps rollouts in HBM; no CUDA device is visible")
         self.T = num_steps
+        # K cost channels (extension; the reference has one): every cost stream is kept channel-major [K, T(+1), N, 1]
+        # so that each channel is the contiguous [T, N] plane the GAE kernel marches over; the un-suffixed attributes
+        # (`costs`, `c_value_preds`, `c_returns`, `c_adv_targ`) are channel 0, i.e. exactly the K = 1 surface
+        self.K = int(num_cost_channels)
         self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.step = 0
         self.N = 0
@@ -41,20 +45,23 @@ class B200RolloutStorage:
         f = dict(device=dev, dtype=torch.float32)
         self.observations = {k: torch.zeros(T + 1, N, *v.shape[1:], device=dev, dtype=v.dtype)
                              for k, v in observations.items()}
+        K = self.K
         self.rewards = torch.zeros(T, N, 1, **f)
-        self.costs = torch.zeros(T, N, 1, **f)
+        self.costs_k = torch.zeros(K, T, N, 1, **f)
         self.value_preds = torch.zeros(T + 1, N, 1, **f)
-        self.c_value_preds = torch.zeros(T + 1, N, 1, **f)
+        self.c_value_preds_k = torch.zeros(K, T + 1, N, 1, **f)
         self.returns = torch.zeros(T + 1, N, 1, **f)
-        self.c_returns = torch.zeros(T + 1, N, 1, **f)
+        self.c_returns_k = torch.zeros(K, T + 1, N, 1, **f)
         self.adv_targ = torch.zeros(T, N, 1, **f)
-        self.c_adv_targ = torch.zeros(T, N, 1, **f)
+        self.c_adv_targ_k = torch.zeros(K, T, N, 1, **f)
+        self.costs, self.c_value_preds = self.costs_k[0], self.c_value_preds_k[0]
+        self.c_returns, self.c_adv_targ = self.c_returns_k[0], self.c_adv_targ_k[0]
         self.action_log_probs = torch.zeros(T, N, 1, **f)
         self.actions = torch.zeros(T, N, device=dev, dtype=torch.int64)
         self.prev_actions = torch.zeros(T + 1, N, device=dev, dtype=torch.int64)
         self.masks = torch.zeros(T + 1, N, 1, **f)
-        self.episode_cost = torch.zeros(N, **f)
-        self.cost_sum_cnt = torch.zeros(2, **f)  # [sum of finished-episode costs, number of finished episodes]
+        self.episode_cost = torch.zeros(K, N, **f)
+        self.cost_sum_cnt = torch.zeros(2 * K, **f)  # per channel: [sum of finished-episode costs, finished episodes]
         self.norm_adv_targ = None
         for k, v in observations.items():
             self.observations[k][0].copy_(v.to(dev), non_blocking=True)
@@ -77,13 +84,16 @@ class B200RolloutStorage:
         self.action_log_probs[t].copy_(action_log_probs.to(dev).reshape(N, 1))
         self.value_preds[t].copy_(value_preds.to(dev).reshape(N, 1))
         self.rewards[t].copy_(rewards.to(dev).reshape(N, 1))
-        if costs is not None:
-            self.costs[t].copy_(costs.to(dev).reshape(N, 1))
+        K = self.K
+        if costs is not None:  # [N, 1] (K = 1) or [N, K]
+            self.costs_k[:, t].copy_(costs.to(dev).reshape(N, K).t().reshape(K, N, 1))
         if c_value_preds is not None:
-            self.c_value_preds[t].copy_(c_value_preds.to(dev).reshape(N, 1))
+            self.c_value_preds_k[:, t].copy_(c_value_preds.to(dev).reshape(N, K).t().reshape(K, N, 1))
         self.masks[t + 1].copy_(masks.to(dev).reshape(N, 1))
         if costs is not None:  # Jc bookkeeping: totals of the episodes that ended at this step
-            ops.episode_cost_step(self.costs[t].view(N), self.masks[t + 1].view(N), self.episode_cost, self.cost_sum_cnt)
+            for k in range(K):
+                ops.episode_cost_step(self.costs_k[k, t].view(N), self.masks[t + 1].view(N), self.episode_cost[k],
+                                      self.cost_sum_cnt[2 * k: 2 * k + 2])
         self.step += 1
 
     def load_rollout(self, ro: Dict, value_preds, c_value_preds, action_log_probs):
@@ -96,21 +106,30 @@ class B200RolloutStorage:
             self.initialize(observations=first, num_samplers=N)
         for k, v in ro["observations"].items():
             self.observations[k].copy_(v, non_blocking=True)
+        K = self.K
         self.rewards.copy_(ro["rewards"], non_blocking=True)
-        self.costs.copy_(ro["costs"], non_blocking=True)
+        if K == 1:
+            self.costs.copy_(ro["costs"], non_blocking=True)
+        else:  # host [T, N, K] -> channel-major planes
+            self.costs_k.copy_(ro["costs"].permute(2, 0, 1).unsqueeze(-1), non_blocking=True)
         self.masks.copy_(ro["masks"], non_blocking=True)
         self.actions.copy_(ro["actions"], non_blocking=True)
         self.prev_actions[1:].copy_(ro["actions"], non_blocking=True)
         self.prev_actions[0].zero_()
         self.value_preds.copy_(value_preds.reshape(self.T + 1, N, 1), non_blocking=True)
-        self.c_value_preds.copy_(c_value_preds.reshape(self.T + 1, N, 1), non_blocking=True)
+        if K == 1:
+            self.c_value_preds.copy_(c_value_preds.reshape(self.T + 1, N, 1), non_blocking=True)
+        else:
+            self.c_value_preds_k.copy_(c_value_preds.reshape(self.T + 1, N, K).permute(2, 0, 1).unsqueeze(-1),
+                                       non_blocking=True)
         self.action_log_probs.copy_(action_log_probs.reshape(self.T, N, 1), non_blocking=True)
-        self.cost_sum_cnt.copy_(torch.stack([ro["episode_cost_sum"], ro["episode_count"]]), non_blocking=True)
+        pair = torch.stack([ro["episode_cost_sum"].reshape(K), ro["episode_count"].reshape(1).expand(K)], 1)
+        self.cost_sum_cnt.copy_(pair.reshape(2 * K), non_blocking=True)
         self.step = self.T
 
     def h2d_bytes(self) -> int:
         n = sum(v.numel() * v.element_size() for v in self.observations.values())
-        for t in (self.rewards, self.costs, self.masks, self.actions, self.value_preds, self.c_value_preds,
+        for t in (self.rewards, self.costs_k, self.masks, self.actions, self.value_preds, self.c_value_preds_k,
                   self.action_log_probs):
             n += t.numel() * t.element_size()
         return n
@@ -129,10 +148,16 @@ class B200RolloutStorage:
             raise NotImplementedError("use_gae=False is not used by the shipped config")
         N = self.N
         self.value_preds[self.T].copy_(next_value.to(self.dev).reshape(N, 1))
-        if next_c_value is not None:
+        K = self.K
+        if next_c_value is not None and K == 1:
             self.c_value_preds[self.T].copy_(next_c_value.to(self.dev).reshape(N, 1))
+        elif next_c_value is not None:  # [N, K] as the cost critic emits it -> channel-major planes
+            self.c_value_preds_k[:, self.T].copy_(next_c_value.to(self.dev).reshape(N, K).t().reshape(K, N, 1).clone())
         ops.gae_dual(self.rewards, self.costs, self.value_preds, self.c_value_preds, self.masks, gamma, tau, gae_algo,
                      out=(self.returns, self.c_returns, self.adv_targ, self.c_adv_targ))
+        for k in range(1, K):  # further cost channels: the same march, one stream per launch
+            ops.gae_dual(self.costs_k[k], None, self.c_value_preds_k[k], None, self.masks, gamma, tau, gae_algo,
+                         out=(self.c_returns_k[k], None, self.c_adv_targ_k[k], None))
         if normalize_advantage:
             self.norm_adv_targ, _ = ops.normalize_advantage(self.adv_targ)
             self.c_norm_adv_targ, _ = ops.normalize_advantage(self.c_adv_targ)
@@ -158,6 +183,10 @@ class B200RolloutStorage:
                 "adv_targ": c(self.adv_targ),
                 "c_adv_targ": c(self.c_adv_targ),
             }
+            if self.K > 1:  # channel-major [K, T, n, 1]
+                ck = (lambda x: x[:, :, sl].contiguous()) if num_mini_batch > 1 else (lambda x: x)
+                batch.update({"c_values": ck(self.c_value_preds_k[:, :T]), "c_returns": ck(self.c_returns_k[:, :T]),
+                              "c_adv_targ": ck(self.c_adv_targ_k)})
             if self.norm_adv_targ is not None:
                 batch["norm_adv_targ"] = c(self.norm_adv_targ)
                 batch["c_norm_adv_targ"] = c(self.c_norm_adv_targ)

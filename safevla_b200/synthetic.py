@@ -26,6 +26,7 @@ class RolloutSpec:
     prompt_tokens: int = 32  # L - 1 ids + EOS
     episode_end_prob: float = 1.0 / 64.0
     seed: int = 1234
+    num_cost_channels: int = 1  # K > 1: costs [T, N, K] (extension beyond the reference's single scalar cost)
 
 
 def encode_goal_ids(ids) -> np.ndarray:
@@ -75,25 +76,30 @@ def make_rollout(spec: RolloutSpec, rank: int = 0, pin: bool = False) -> Dict[st
 
     terminal = done[1:]  # step t is terminal iff a new episode starts at t+1
     rewards = (10.0 * (torch.rand(T, N, generator=g) < 0.3).float() * terminal.float()).unsqueeze(-1)
-    costs = (torch.rand(T, N, 5, generator=g) < 0.05).float().sum(-1, keepdim=True)
+    K = spec.num_cost_channels
+    if K == 1:
+        costs = (torch.rand(T, N, 5, generator=g) < 0.05).float().sum(-1, keepdim=True)
+    else:
+        costs = (torch.rand(T, N, K, 5, generator=g) < 0.05).float().sum(-1)
     actions = torch.randint(0, A, (T, N), generator=g)
 
-    # Jc bookkeeping: undiscounted cost of episodes that *finish* inside the rollout
-    ep_cost = torch.zeros(N)
-    cost_sum, ep_cnt = 0.0, 0
+    # Jc bookkeeping: undiscounted cost of episodes that *finish* inside the rollout (per cost channel)
+    ep_cost = torch.zeros(N, K)
+    cost_sum, ep_cnt = torch.zeros(K), 0
     for t in range(T):
-        ep_cost += costs[t, :, 0]
+        ep_cost += costs[t]
         fin = terminal[t]
-        cost_sum += float(ep_cost[fin].sum())
+        cost_sum += ep_cost[fin].sum(0)
         ep_cnt += int(fin.sum())
         ep_cost[fin] = 0.0
+    cost_sum = float(cost_sum[0]) if K == 1 else cost_sum
     out = {
         "observations": obs,
         "masks": masks,
         "rewards": rewards,
         "costs": costs,
         "actions": actions,
-        "episode_cost_sum": torch.tensor(cost_sum, dtype=torch.float32),
+        "episode_cost_sum": torch.as_tensor(cost_sum, dtype=torch.float32),
         "episode_count": torch.tensor(float(ep_cnt), dtype=torch.float32),
     }
     if pin and torch.cuda.is_available():

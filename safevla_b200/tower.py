@@ -314,8 +314,9 @@ class Tower:
             out["logits"] = ops.gemm(b_tn, W.p("actor.linear.weight"), self._new(Md, self.A, dtype=f32),
                                      bias=W.p("actor.linear.bias")).view(T, N, self.A)
         if want_values:
-            out["values"] = ops.gemm(b_tn, W.p("critic.fc.weight"), self._new(Md, 1, dtype=f32),
-                                     bias=W.p("critic.fc.bias")).view(T, N, 1)
+            nv = W.p("critic.fc.weight").shape[0]  # 1, or K for the cost tower of the K-cost-channel extension
+            out["values"] = ops.gemm(b_tn, W.p("critic.fc.weight"), self._new(Md, nv, dtype=f32),
+                                     bias=W.p("critic.fc.bias")).view(T, N, nv)
         if keep:
             t.update({"hf": h, "rf": rf, "yf": yf, "b_tn": b_tn})
         return out, t
@@ -355,8 +356,9 @@ class Tower:
             out["logits"] = ops.gemm(b, W.p("actor.linear.weight"), self._new(N, self.A, dtype=f32),
                                      bias=W.p("actor.linear.bias")).view(1, N, self.A)
         if want_values:
-            out["values"] = ops.gemm(b, W.p("critic.fc.weight"), self._new(N, 1, dtype=f32),
-                                     bias=W.p("critic.fc.bias")).view(1, N, 1)
+            nv = W.p("critic.fc.weight").shape[0]
+            out["values"] = ops.gemm(b, W.p("critic.fc.weight"), self._new(N, nv, dtype=f32),
+                                     bias=W.p("critic.fc.bias")).view(1, N, nv)
         return out
 
     def decoder_bwd(self, dlogits, dvalues, t, prev_actions, masks, in_hand, traj_nt, perm_nt, T, N):
@@ -374,7 +376,7 @@ class Tower:
             ops.colsum(dl, W.g("actor.linear.bias"), accumulate=True)
             db_tn = ops.gemm(dl, W.p("actor.linear.weight"), self._new(Md, D, dtype=f32), trans_b=False)
         if dvalues is not None:
-            dv = dvalues.view(Md, 1)
+            dv = dvalues.view(Md, -1)
             ops.gemm(dv, t["b_tn"], W.g("critic.fc.weight"), trans_a=True, trans_b=False, accumulate=True)
             ops.colsum(dv, W.g("critic.fc.bias"), accumulate=True)
             db_tn = ops.gemm(dv, W.p("critic.fc.weight"), self._new(Md, D, dtype=f32), trans_b=False,

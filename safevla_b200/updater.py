@@ -44,8 +44,9 @@ class PPOLagConfig:
     eps: float = 1e-8
     # stage 0 = ["ppo_value_loss", "safe_ppo_value_loss"]; stage 1 = ["ppo_log_loss"] (:348-378)
     stage: int = 1
-    # omnisafe Lagrange defaults + README cost limit
-    cost_limit: float = 2.31964
+    # omnisafe Lagrange defaults + README cost limit; a tuple = one limit per cost channel (K-channel
+    # extension: the model and the storage must be built with the same num_cost_channels)
+    cost_limit: object = 2.31964
     lambda_init: float = 0.001
     lambda_lr: float = 0.035
     lambda_upper_bound: Optional[float] = None
@@ -90,7 +91,10 @@ class PPOLagUpdater:
         m, c = self.model, self.cfg
         T, N = storage.T, storage.N
         R = T * N
-        storage.before_updates(next_value=storage.value_preds[T], next_c_value=storage.c_value_preds[T],
+        K = storage.K
+        assert K == self.lagrange.K == m.K, "storage, model and cost limits must agree on the number of cost channels"
+        # the bootstrap rows (value / cost-value predictions of the step after the rollout) are already in the arena
+        storage.before_updates(next_value=storage.value_preds[T], next_c_value=None,
                                use_gae=True, gamma=c.gamma, tau=c.gae_lambda)
         obs = {k: v[:T] for k, v in storage.observations.items()}
         rc = m.prepare(obs, T, N)
@@ -108,24 +112,40 @@ class PPOLagUpdater:
                 o, st = m.tower_forward(idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR),
                                         want_values=(idx != ACTOR))
                 outs[idx], states[idx] = o, st
-            if c.stage == 0:
+            if c.stage == 0 and K == 1:
                 scal, _, dv, dcv = ops.ppo_lag_fwd_bwd(
                     None, None, None, None, None, outs[CRITIC]["values"], storage.returns[:T],
                     outs[COST]["values"], storage.c_returns[:T], None, hp,
                     old_values=storage.value_preds[:T], old_c_values=storage.c_value_preds[:T])
                 m.tower_backward(CRITIC, states[CRITIC], None, dv)
                 m.tower_backward(COST, states[COST], None, dcv)
+            elif c.stage == 0:
+                # K cost channels: the cost critic's head emits [T, N, K]; its loss is the SUM over channels of the
+                # per-channel SafePPOValue means (inv_count stays 1 / R), evaluated over the R * K flattened entries
+                scal, _, dv, _ = ops.ppo_lag_fwd_bwd(None, None, None, None, None, outs[CRITIC]["values"],
+                                                     storage.returns[:T], None, None, None, hp,
+                                                     old_values=storage.value_preds[:T])
+                tnk = lambda x: x.reshape(K, R).t().contiguous()  # noqa: E731  channel-major -> the head's [R, K]
+                scal_c, _, _, dcv = ops.ppo_lag_fwd_bwd(None, None, None, None, None, None, None, outs[COST]["values"],
+                                                        tnk(storage.c_returns_k[:, :T]), None, hp,
+                                                        old_c_values=tnk(storage.c_value_preds_k[:, :T]))
+                m.tower_backward(CRITIC, states[CRITIC], None, dv)
+                m.tower_backward(COST, states[COST], None, dcv)
+                scal = torch.cat([scal[0:4], scal_c[4:5], scal[5:]])  # [0] value-critic total, [4] cost-critic total
             else:
+                c_adv, lam = storage.c_adv_targ, self.lagrange.lagrangian_multiplier
+                if K > 1:  # fold the K (advantage, multiplier) pairs into the one pair the fused loss takes
+                    c_adv, lam = ops.combine_cost_advantages(storage.c_adv_targ_k.view(K, R), lam)
                 scal, dl, dv, _ = ops.ppo_lag_fwd_bwd(
                     outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, storage.adv_targ,
-                    storage.c_adv_targ, outs[CRITIC]["values"], storage.returns[:T], None, None,
-                    self.lagrange.lagrangian_multiplier, hp, old_values=storage.value_preds[:T])
+                    c_adv, outs[CRITIC]["values"], storage.returns[:T], None, None,
+                    lam, hp, old_values=storage.value_preds[:T])
                 m.tower_backward(ACTOR, states[ACTOR], dl, None)
                 m.tower_backward(CRITIC, states[CRITIC], None, dv)
             del states
             self._reduce_clip_step(storage, last=(rep == c.update_repeats - 1))
         # lambda <- proj(lambda + Adam step on (Jc - d)); Jc from the (all-reduced) finished-episode costs
-        cost_pair = self.comm[-self.TAIL:-self.TAIL + 2] if self.world > 1 else storage.cost_sum_cnt
+        cost_pair = self.comm[-self.TAIL:-self.TAIL + 2 * K] if self.world > 1 else storage.cost_sum_cnt
         self.lagrange.update_from_sum_count(cost_pair)
         return {"loss_scalars": scal, "lambda": self.lagrange.lagrangian_multiplier, "grad_sq_norm": self.sq}
 

@@ -342,3 +342,20 @@ def test_goal_byte_codec_matches_reference_encoding():
         assert convert_byte_to_string(mine) == ref.view("S1000")[0].decode(errors="ignore") or len(s.encode()) > 1000
     r = SafeRLStepResult({"a": 1}, 1.0, 0.0, False, {})
     assert r._fields == ("observation", "reward", "cost", "done", "info")  # tasks/abstract_task.py:369-380
+
+
+def test_cost_channel_extension_contract():
+    """K cost channels only widen the cost critic's head and the cost arrays; K = 1 is the reference key for key."""
+    sd1, sd2 = init_state_dict(6, 1, 3), init_state_dict(6, 1, 3, num_cost_channels=2)
+    assert list(sd1) == list(sd2)
+    for k in sd1:
+        if k.startswith("c_critic_tsfm.critic.fc"):
+            assert sd2[k].shape[0] == 2 and sd1[k].shape[0] == 1
+        else:
+            assert torch.equal(sd1[k], sd2[k]), k
+    assert ParamLayout(6, 1, 2).total - ParamLayout(6, 1).total == 512
+    from safevla_b200.synthetic import RolloutSpec, make_rollout
+    r1 = make_rollout(RolloutSpec(6, 2, 6, 1, seed=5))
+    r2 = make_rollout(RolloutSpec(6, 2, 6, 1, seed=5, num_cost_channels=2))
+    assert r1["costs"].shape == (6, 2, 1) and r2["costs"].shape == (6, 2, 2) and r2["episode_cost_sum"].shape == (2,)
+    assert torch.equal(r1["masks"], r2["masks"]) and torch.equal(r1["rewards"], r2["rewards"])

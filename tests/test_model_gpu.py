@@ -161,6 +161,63 @@ def test_updater_matches_oracle_update(dev):
     assert worst[1] < 2e-5, worst
 
 
+@pytest.mark.parametrize("stage", [1, 0])
+def test_two_cost_channels_update_matches_oracle(dev, stage):
+    """K = 2 cost channels (BASELINE config 5's "dual cost channels"; an extension beyond the reference's scalar cost):
+    per-channel GAE, (A - sum_k lam_k A_c,k) / (1 + sum_k lam_k), a two-output cost critic and two independently
+    projected multipliers -- the whole update against the CPU oracle."""
+    from oracle.update_oracle import oracle_update
+    from safevla_b200.model import B200SafeActorCritic
+    from safevla_b200.storage import B200RolloutStorage
+    from safevla_b200.synthetic import RolloutSpec, make_rollout
+    from safevla_b200.updater import PPOLagConfig, PPOLagUpdater
+    T, N, A, C, K = 8, 4, 6, 2, 2
+    sd = init_state_dict(A, C, seed=23, actor_gain=1.0, num_cost_channels=K)
+    ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.25, seed=78, num_cost_channels=K))
+    assert ro["costs"].shape == (T, N, K) and ro["episode_cost_sum"].shape == (K,)
+    g = torch.Generator().manual_seed(6)
+    vp, cvp = torch.randn(T + 1, N, 1, generator=g), torch.randn(T + 1, N, K, generator=g).abs()
+    logp = -1.7 + 0.1 * torch.randn(T, N, generator=g)
+    # one limit below and one far above the observed episode costs: lambda_0 grows, lambda_1 shrinks
+    cfg = PPOLagConfig(update_repeats=2, lr=1e-3, eps=1e-4, stage=stage, cost_limit=(0.05, 50.0), lambda_init=0.4)
+    ref_sd, ref_lams, ref_info = oracle_update(sd, ro, vp, cvp, logp, cfg, A, C)
+    model = B200SafeActorCritic(A, C, precision="fp32", state_dict=sd, device=dev, num_cost_channels=K)
+    st = B200RolloutStorage(T, dev, num_cost_channels=K)
+    st.load_rollout(ro, vp, cvp, logp)
+    upd = PPOLagUpdater(model, cfg)
+    res = upd.update(st)
+    lam = res["lambda"].cpu()
+    assert lam.shape == (K,) and abs(lam[0].item() - ref_lams[0]) < 1e-5 and abs(lam[1].item() - ref_lams[1]) < 1e-5
+    assert lam[0].item() > 0.4 > lam[1].item()
+    # per-channel GAE is the bit-exact sequential recursion
+    for k in range(K):
+        cret, cadv = TO.gae_returns(ro["costs"][..., k:k + 1], cvp[..., k:k + 1], ro["masks"], 0.99, 0.95)
+        assert torch.equal(st.c_returns_k[k].cpu(), cret) and torch.equal(st.c_adv_targ_k[k].cpu(), cadv)
+    mine = model.state_dict()
+    assert mine["c_critic_tsfm.critic.fc.weight"].shape == (K, 512)
+    worst, moved = ("", 0.0), 0.0
+    for k, v in ref_sd.items():
+        if "text_encoder" in k:
+            continue
+        err = (mine[k].cpu() - v).abs().max().item()
+        moved = max(moved, (v - sd[k]).abs().max().item())
+        if err > worst[1]:
+            worst = (k, err)
+    assert moved > 5e-4 and worst[1] < 2e-5, worst
+
+
+def test_combine_cost_advantages_kernel(dev):
+    from safevla_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for K, R in ((2, 4096), (3, 1028), (1, 77), (8, 64)):
+        ca = torch.randn(K, R, generator=g).to(dev)
+        for lam in (torch.rand(K, generator=g), torch.zeros(K)):
+            out, le = ops.combine_cost_advantages(ca, lam.to(dev))
+            L = lam.sum().item()
+            exp = (lam.to(dev)[:, None] * ca).sum(0) / L if L > 0 else torch.zeros(R, device=dev)
+            assert abs(le.item() - L) < 1e-6 and torch.allclose(out, exp, atol=1e-6, rtol=1e-5)
+
+
 # ------------------------------------------------------------------------------------------ rollout-side T = 1
 @pytest.mark.parametrize("name", ["step_N3_A6_C1", "step_N2_A20_C2"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

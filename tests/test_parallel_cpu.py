@@ -29,10 +29,14 @@ def _worker(rank, world, port, out):
     scale = allreduce_arena(comm, n, cost)
     lo, hi = shard_samplers(64, world, rank)
     out[rank] = (comm.clone(), scale, lo, hi)
+    # K = 2 cost channels: two (sum, count) pairs ride in the same tail
+    comm[:n] = local
+    allreduce_arena(comm, n, torch.tensor([1.0 + rank, 2.0, 10.0 * (rank + 1), 2.0]))
+    out[10 + rank] = comm[n:n + 4].clone()
     # a non-final repeat zeroes the tail so stale sums never leak into lambda
     comm[:n] = local
     allreduce_arena(comm, n, None)
-    assert comm[n:n + 2].abs().sum() == 0
+    assert comm[n:].abs().sum() == 0
     dist.destroy_process_group()
 
 
@@ -49,6 +53,7 @@ def test_single_allreduce_carries_grads_and_cost_scalars():
         assert comm[1000].item() == 7.0 and comm[1001].item() == 4.0  # sum of costs, episode count
         assert (lo, hi) == (r * 32, (r + 1) * 32)
     assert torch.equal(out[0][0], out[1][0])  # identical on every rank -> identical lambda without a broadcast
+    assert out[10].tolist() == out[11].tolist() == [3.0, 4.0, 30.0, 4.0]
 
 
 def test_shard_samplers_rejects_ragged():
