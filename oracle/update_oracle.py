@@ -21,7 +21,7 @@ def oracle_update(sd: Dict[str, torch.Tensor], ro: Dict, value_preds, c_value_pr
     prev = torch.cat([torch.zeros_like(ro["actions"][:1]), ro["actions"][:-1]], 0)
     masks = ro["masks"][:T]
     ret, adv = TO.gae_returns(ro["rewards"], value_preds, ro["masks"], cfg.gamma, cfg.gae_lambda)
-    # K cost channels (K = 1: the reference; K > 1: the extension of DESIGN.md section 8): one GAE per channel
+    # K cost channels (K = 1: the reference; K > 1: the extension of DESIGN.md section 7): one GAE per channel
     K = ro["costs"].shape[-1]
     c_value_preds = c_value_preds.reshape(T + 1, -1, K)
     chan = [TO.gae_returns(ro["costs"][..., k:k + 1], c_value_preds[..., k:k + 1], ro["masks"], cfg.gamma,
