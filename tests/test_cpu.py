@@ -359,3 +359,25 @@ def test_cost_channel_extension_contract():
     r2 = make_rollout(RolloutSpec(6, 2, 6, 1, seed=5, num_cost_channels=2))
     assert r1["costs"].shape == (6, 2, 1) and r2["costs"].shape == (6, 2, 2) and r2["episode_cost_sum"].shape == (2,)
     assert torch.equal(r1["masks"], r2["masks"]) and torch.equal(r1["rewards"], r2["rewards"])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm) runs on host cores only and prints ONE JSON line with
+    the base-contract keys, `impl`, a `cpu_baseline` describing the run and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "ppo_lagrangian_update_samples_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "cfg2_64env_128step" and d["vs_baseline"] is None
