@@ -32,7 +32,7 @@ namespace {
 template <int BN, bool AMN, bool BMN>
 __global__ void __launch_bounds__(kThreads, 1)
 svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const __grid_constant__ CUtensorMap mapC, TcArgs g) {
+                    const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapC2, TcArgs g) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -55,6 +55,7 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC2) : "memory");
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages; ++s) {
@@ -188,9 +189,9 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         uint8_t* stg = stage_base + (warp - kEpiWarp0) * kStgBytes;
         if (!staged) epilogue_direct(g, taddr, m, row_ok, tn * BN, cb, ce, sp);
         else if (dtC == SVLA_F32)
-          epilogue_staged_t<true>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane, pre, next_m0, next_nt0);
+          epilogue_staged_t<true>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane, pre, next_m0, next_nt0, &mapC2);
         else
-          epilogue_staged_t<false>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane, pre, next_m0, next_nt0);
+          epilogue_staged_t<false>(g, &mapC, stg, taddr, tm * BM + q * 32, tn * BN, cb, ce, sp, lane, pre, next_m0, next_nt0, &mapC2);
       }
       tc_fence_before();
       __syncwarp();
@@ -290,8 +291,8 @@ int make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, 
 }
 
 template <int BN, bool AMN, bool BMN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcArgs& g, int grid,
-              cudaStream_t st) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mc2, const TcArgs& g,
+              int grid, cudaStream_t st) {
   constexpr int kStages = (BN == 256) ? 4 : 6;
   constexpr size_t smem = (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024 + 8 * kStgBytes + 512;
   auto kern = svla_gemm_tc_kernel<BN, AMN, BMN>;
@@ -300,7 +301,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
     SVLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, st>>>(ma, mb, mc, g);
+  kern<<<grid, kThreads, smem, st>>>(ma, mb, mc, mc2, g);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
@@ -393,22 +394,27 @@ int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
 
   // output tiles leave through TMA stores (32 x 32 boxes out of the swizzled staging tile) unless this launch
   // writes split-K partials
-  CUtensorMap mc = ma;
+  CUtensorMap mc = ma, mc2 = ma;
   g.tma_store = 0;
   if (g.splits == 1) {
     rc = make_tmap(ctx, d->C, d->N, d->M, d->ldc, 32, 32, &mc, d->dtypeC == SVLA_F32 ? 2 : 1);
     if (rc) return rc;
+    mc2 = mc;
+    if (d->dtypeC == SVLA_BF16) {  // 64-column blocks: [32 rows x 128 B] boxes, 128B swizzle
+      rc = make_tmap(ctx, d->C, d->N, d->M, d->ldc, 64, 32, &mc2, 0);
+      if (rc) return rc;
+    }
     g.tma_store = 1;
   }
   const int grid = std::min(tiles * g.splits, ctx->sm_count);
   if (BN == 256) {
-    if (!amn && !bmn) rc = launch_tc<256, false, false>(ma, mb, mc, g, grid, st);
-    else if (!amn && bmn) rc = launch_tc<256, false, true>(ma, mb, mc, g, grid, st);
-    else rc = launch_tc<256, true, true>(ma, mb, mc, g, grid, st);
+    if (!amn && !bmn) rc = launch_tc<256, false, false>(ma, mb, mc, mc2, g, grid, st);
+    else if (!amn && bmn) rc = launch_tc<256, false, true>(ma, mb, mc, mc2, g, grid, st);
+    else rc = launch_tc<256, true, true>(ma, mb, mc, mc2, g, grid, st);
   } else {
-    if (!amn && !bmn) rc = launch_tc<128, false, false>(ma, mb, mc, g, grid, st);
-    else if (!amn && bmn) rc = launch_tc<128, false, true>(ma, mb, mc, g, grid, st);
-    else rc = launch_tc<128, true, true>(ma, mb, mc, g, grid, st);
+    if (!amn && !bmn) rc = launch_tc<128, false, false>(ma, mb, mc, mc2, g, grid, st);
+    else if (!amn && bmn) rc = launch_tc<128, false, true>(ma, mb, mc, mc2, g, grid, st);
+    else rc = launch_tc<128, true, true>(ma, mb, mc, mc2, g, grid, st);
   }
   if (rc) return rc;
   if (g.splits > 1) {

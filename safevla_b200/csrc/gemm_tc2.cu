@@ -68,7 +68,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 template <bool AMN, bool BMN, bool ASUM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                     const __grid_constant__ CUtensorMap mapC, TcArgs g) {
+                     const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapC2, TcArgs g) {
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = (BN2 / 2) * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;  // 32 KB per CTA
   constexpr uint32_t kTmemCols = 2 * BN2;
@@ -97,6 +97,7 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC2) : "memory");
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages2; ++s) {
@@ -245,9 +246,9 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         uint8_t* stg = stage_base + (warp - kEpiWarp0) * kStgBytes;
         if (!staged) epilogue_direct(g, taddr, m, row_ok, tn * BN2, cb, ce, sp);
         else if (dtC == SVLA_F32)
-          epilogue_staged_t<true>(g, &mapC, stg, taddr, m0, tn * BN2, cb, ce, sp, lane, pre, next_m0, next_nt0);
+          epilogue_staged_t<true>(g, &mapC, stg, taddr, m0, tn * BN2, cb, ce, sp, lane, pre, next_m0, next_nt0, &mapC2);
         else
-          epilogue_staged_t<false>(g, &mapC, stg, taddr, m0, tn * BN2, cb, ce, sp, lane, pre, next_m0, next_nt0);
+          epilogue_staged_t<false>(g, &mapC, stg, taddr, m0, tn * BN2, cb, ce, sp, lane, pre, next_m0, next_nt0, &mapC2);
         if (ASUM && g.asum != nullptr && tn == 0 && half == 0) {  // every column of the ones-product is the row sum
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kSumCol, r);
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(256) tc2_splitk_reduce_kernel(TcArgs g) {
 }
 
 template <bool AMN, bool BMN, bool ASUM>
-int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcArgs& g, int grid,
-               cudaStream_t st) {
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mc2, const TcArgs& g,
+               int grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)kStages2 * (BM * BK * 2 + (BN2 / 2) * BK * 2) + 1024 + 8 * kStgBytes + 512;
   auto kern = svla_gemm_tc2_kernel<AMN, BMN, ASUM>;
   static bool attr_set = false;
@@ -309,7 +310,7 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     SVLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, st>>>(ma, mb, mc, g);  // cluster shape comes from __cluster_dims__
+  kern<<<grid, kThreads, smem, st>>>(ma, mb, mc, mc2, g);  // cluster shape comes from __cluster_dims__
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
@@ -369,17 +370,23 @@ int svla_gemm_tc2(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   else rc = svla_make_tmap(ctx, d->B, d->N, d->K, d->ldb, 64, BK, &mb, 0);            // [K rows][N]  box {64, 64}
   if (rc) return rc;
   mc = ma;
+  CUtensorMap mc2 = ma;
   g.tma_store = 0;
   if (g.splits == 1) {
     rc = svla_make_tmap(ctx, d->C, d->N, d->M, d->ldc, 32, 32, &mc, d->dtypeC == SVLA_F32 ? 2 : 1);
     if (rc) return rc;
+    mc2 = mc;
+    if (d->dtypeC == SVLA_BF16) {  // 64-column blocks: [32 rows x 128 B] boxes, 128B swizzle
+      rc = svla_make_tmap(ctx, d->C, d->N, d->M, d->ldc, 64, 32, &mc2, 0);
+      if (rc) return rc;
+    }
     g.tma_store = 1;
   }
   const int grid = 2 * std::min(tiles * g.splits, clusters);
-  if (!amn && !bmn) rc = launch_tc2<false, false, false>(ma, mb, mc, g, grid, st);
-  else if (!amn && bmn) rc = launch_tc2<false, true, false>(ma, mb, mc, g, grid, st);
-  else if (g.asum) rc = launch_tc2<true, true, true>(ma, mb, mc, g, grid, st);
-  else rc = launch_tc2<true, true, false>(ma, mb, mc, g, grid, st);
+  if (!amn && !bmn) rc = launch_tc2<false, false, false>(ma, mb, mc, mc2, g, grid, st);
+  else if (!amn && bmn) rc = launch_tc2<false, true, false>(ma, mb, mc, mc2, g, grid, st);
+  else if (g.asum) rc = launch_tc2<true, true, true>(ma, mb, mc, mc2, g, grid, st);
+  else rc = launch_tc2<true, true, false>(ma, mb, mc, mc2, g, grid, st);
   if (rc) return rc;
   if (g.splits > 1) {
     const long long total = (long long)d->M * d->N;

@@ -417,11 +417,83 @@ __device__ __forceinline__ void epilogue_staged_impl(const TcArgs& g, const CUte
   // caller may release the TMEM accumulator while the last stores are still in flight
 }
 
+// ---- 64-column blocks (bf16 outputs without a side operand: plain / bias / ReLU / GELU) -----------------------------
+// The per-chunk fixed costs (store-buffer wait, warp syncs, the proxy fence with its MEMBAR, the TMA issue) are paid
+// once per 64 columns instead of once per 32: two LDTMs are in flight together, the 32 x 128 B staging tile (128B
+// swizzle, the warp's whole 4 KB) leaves through ONE TMA store of full 128-byte row segments.
+template <int EPI, bool BIAS>
+__device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensorMap* mapC2, uint8_t* stg0, uint32_t taddr,
+                                                 int m0, int ntile0, int c_begin, int c_end, int lane) {
+  const uint32_t stg_s = smem_u32(stg0);
+#pragma unroll 1
+  for (int cb = c_begin; cb < c_end; cb += 64) {
+    const int n0 = ntile0 + cb;
+    if (n0 >= g.N) break;  // warp-uniform (N is a multiple of 64)
+    uint32_t r0[32], r1[32];
+    tmem_ld32(taddr + cb, r0);
+    tmem_ld32(taddr + cb + 32, r1);
+    float b0 = 0.f, b1 = 0.f;
+    if (BIAS) {
+      b0 = __ldg(g.bias + n0 + lane);
+      b1 = __ldg(g.bias + n0 + 32 + lane);
+    }
+    tmem_wait_ld();
+    if (g.alpha != 1.f) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        r0[e] = __float_as_uint(__uint_as_float(r0[e]) * g.alpha);
+        r1[e] = __float_as_uint(__uint_as_float(r1[e]) * g.alpha);
+      }
+    }
+    if (BIAS) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        r0[e] = __float_as_uint(__uint_as_float(r0[e]) + __shfl_sync(0xffffffffu, b0, e));
+        r1[e] = __float_as_uint(__uint_as_float(r1[e]) + __shfl_sync(0xffffffffu, b1, e));
+      }
+    }
+    if (EPI == SVLA_EPI_GELU) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        r0[e] = __float_as_uint(gelu_erf(__uint_as_float(r0[e])));
+        r1[e] = __float_as_uint(gelu_erf(__uint_as_float(r1[e])));
+      }
+    }
+    // the store that last read the staging tile must be done reading it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t* r = j < 4 ? r0 : r1;
+      const int jj = j & 3;
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]), __uint_as_float(r[jj * 8 + 2 * e + 1]));
+      if (EPI == SVLA_EPI_RELU) {
+        const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], z);
+      }
+      sts128(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(mapC2), "r"(stg_s),
+                   "r"(n0), "r"(m0)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+}
+
 // dispatch on the (warp-uniform) flag combination; the listed ones are every combination the towers launch
 template <bool F32>
 __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtensorMap* mapC, uint8_t* stg0, uint32_t taddr,
                                                   int m0, int ntile0, int c_begin, int c_end, int sp, int lane,
-                                                  SidePre& pre, int next_m0, int next_ntile0) {
+                                                  SidePre& pre, int next_m0, int next_ntile0, const CUtensorMap* mapC2) {
 #define SVLA_EPI_CALL(E, B, R, A) \
   epilogue_staged_impl<F32, E, B, R, A>(g, mapC, stg0, taddr, m0, ntile0, c_begin, c_end, sp, lane, pre, next_m0, next_ntile0)
   const bool b = g.bias != nullptr, rs = g.residual != nullptr, ac = g.accumulate != 0;
@@ -433,7 +505,12 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
     else if (e == SVLA_EPI_NONE && !b && !rs && !ac) SVLA_EPI_CALL(SVLA_EPI_NONE, false, false, false);
     else SVLA_EPI_CALL(-1, false, false, false);
   } else {
+    const bool blk = g.tma_store && !rs && !ac && e != SVLA_EPI_RELU_MASK && g.dbg != 9;  // 64-column blocks
     if (ac) SVLA_EPI_CALL(-1, false, false, false);
+    else if (blk && e == SVLA_EPI_NONE && b) epilogue_block64<SVLA_EPI_NONE, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (blk && e == SVLA_EPI_NONE && !b) epilogue_block64<SVLA_EPI_NONE, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (blk && e == SVLA_EPI_RELU && b) epilogue_block64<SVLA_EPI_RELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (blk && e == SVLA_EPI_GELU && b) epilogue_block64<SVLA_EPI_GELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
     else if (e == SVLA_EPI_NONE && b && !rs) SVLA_EPI_CALL(SVLA_EPI_NONE, true, false, false);
     else if (e == SVLA_EPI_RELU && b && !rs) SVLA_EPI_CALL(SVLA_EPI_RELU, true, false, false);
     else if (e == SVLA_EPI_NONE && b && rs) SVLA_EPI_CALL(SVLA_EPI_NONE, true, true, false);
