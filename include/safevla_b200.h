@@ -72,6 +72,13 @@ int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* costs, const
 int svla_normalize_advantage(svla_ctx* ctx, const float* adv, float* norm_adv, float* stats,
                              long long n, svla_stream stream);
 
+/* The same normalisation in two phases for data-parallel runs: sums[0..2] = {sum adv,
+ * sum adv^2, n} of the local shard; the host all-reduces the three floats; every rank then normalises with the GLOBAL
+ * mean / unbiased std (written to stats[0..1]). */
+int svla_advantage_sums(svla_ctx* ctx, const float* adv, long long n, float* sums, svla_stream stream);
+int svla_normalize_advantage_from_sums(svla_ctx* ctx, const float* adv, float* norm_adv, const float* sums,
+                                       float* stats, long long n, svla_stream stream);
+
 typedef struct {
   float clip_param;     /* training/online/loss/customized_loss.py:342 */
   float w_action;       /* action_loss_schedule(step) :394 */

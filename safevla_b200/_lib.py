@@ -65,6 +65,8 @@ PROTOTYPES: Dict[str, list] = {
     "svla_launch_count": [],
     "svla_gae_dual": [c_p] + [c_p] * 9 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_p],
     "svla_normalize_advantage": [c_p, c_p, c_p, c_p, c_ll, c_p],
+    "svla_advantage_sums": [c_p, c_p, c_ll, c_p, c_p],
+    "svla_normalize_advantage_from_sums": [c_p, c_p, c_p, c_p, c_p, c_ll, c_p],
     "svla_ppo_lag_fwd_bwd": [c_p] + [c_p] * 12 + [C.POINTER(PpoHparams)] + [c_p] * 4 + [c_ll, C.c_int, c_p],
     "svla_lagrange_update": [c_p, c_p, c_p, c_p, C.c_float, C.c_float, C.c_float, c_p],
     "svla_sq_norm": [c_p, c_p, c_ll, c_p, c_p],

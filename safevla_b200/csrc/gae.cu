@@ -12,6 +12,8 @@
 //   * warp scan: one warp per sampler, each lane owns a block of consecutive steps; the
 //     recursion is the affine map g -> delta + a*g, composed with a warp suffix scan.
 //     For small N (BASELINE shapes: 64 samplers), where the march has no parallelism.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -326,6 +328,29 @@ __global__ void adv_stats_final(const float* partials, int nb, long long n, floa
   }
   (void)red;
 }
+// split form for data-parallel runs: sums[0..2] = {sum x, sum x^2, n}; the host all-reduces the three floats, then
+// every rank derives the GLOBAL mean / unbiased std from them
+__global__ void adv_sums_final(const float* partials, int nb, long long n, float* sums) {
+  if (threadIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nb; ++i) {
+      s += partials[2 * i];
+      q += partials[2 * i + 1];
+    }
+    sums[0] = (float)s;
+    sums[1] = (float)q;
+    sums[2] = (float)n;
+  }
+}
+__global__ void adv_stats_from_sums(const float* sums, float* stats) {
+  if (threadIdx.x == 0) {
+    const double s = sums[0], q = sums[1], n = sums[2];
+    const double mean = n > 0.0 ? s / n : 0.0;
+    const double var = n > 1.0 ? (q - n * mean * mean) / (n - 1.0) : 0.0;
+    stats[0] = (float)mean;
+    stats[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+  }
+}
 __global__ void __launch_bounds__(256) adv_normalize(const float* x, float* y, long long n, const float* stats) {
   const float mean = stats[0], inv = 1.f / (stats[1] + 1e-5f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -434,6 +459,30 @@ extern "C" int svla_normalize_advantage(svla_ctx* ctx, const float* adv, float* 
   SVLA_LAUNCH_CHECK();
   adv_stats_final<<<1, 32, 0, as_stream(stream)>>>(ctx->partials, nb, n, stats);
   SVLA_LAUNCH_CHECK();
+  adv_normalize<<<nb, 256, 0, as_stream(stream)>>>(adv, norm_adv, n, stats);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+extern "C" int svla_advantage_sums(svla_ctx* ctx, const float* adv, long long n, float* sums, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && adv && sums, "NULL argument");
+  int nb = (int)((std::max<long long>(n, 1) + 255) / 256);
+  if (nb > 1024) nb = 1024;
+  adv_stats_partial<<<nb, 256, 0, as_stream(stream)>>>(adv, n, ctx->partials);
+  SVLA_LAUNCH_CHECK();
+  adv_sums_final<<<1, 32, 0, as_stream(stream)>>>(ctx->partials, nb, n, sums);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+extern "C" int svla_normalize_advantage_from_sums(svla_ctx* ctx, const float* adv, float* norm_adv, const float* sums,
+                                                  float* stats, long long n, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && adv && norm_adv && sums && stats, "NULL argument");
+  adv_stats_from_sums<<<1, 32, 0, as_stream(stream)>>>(sums, stats);
+  SVLA_LAUNCH_CHECK();
+  if (n <= 0) return SVLA_OK;
+  int nb = (int)((n + 255) / 256);
+  if (nb > 1024) nb = 1024;
   adv_normalize<<<nb, 256, 0, as_stream(stream)>>>(adv, norm_adv, n, stats);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;

@@ -53,6 +53,24 @@ def normalize_advantage(adv: torch.Tensor):
     return out, stats
 
 
+def advantage_sums(adv: torch.Tensor) -> torch.Tensor:
+    """[sum adv, sum adv^2, n] of the local shard (fp32 device tensor) -- all-reduce it, then normalise with
+    `normalize_advantage_from_sums` so every rank uses the global statistics."""
+    _cuda(adv)
+    sums = torch.empty(3, device=adv.device, dtype=torch.float32)
+    check(_lib().svla_advantage_sums(get_ctx(), ptr(adv), adv.numel(), ptr(sums), stream_ptr()), "svla_advantage_sums")
+    return sums
+
+
+def normalize_advantage_from_sums(adv: torch.Tensor, sums: torch.Tensor):
+    _cuda(adv, sums)
+    out = torch.empty_like(adv)
+    stats = torch.empty(2, device=adv.device, dtype=torch.float32)
+    check(_lib().svla_normalize_advantage_from_sums(get_ctx(), ptr(adv), ptr(out), ptr(sums), ptr(stats), adv.numel(),
+                                                    stream_ptr()), "svla_normalize_advantage_from_sums")
+    return out, stats
+
+
 def ppo_lag_fwd_bwd(logits, actions, old_logp, adv, c_adv, values, returns, c_values, c_returns, lambda_dev,
                     hp: L.PpoHparams, old_values=None, old_c_values=None, want_grads: bool = True):
     """Returns (scalars[16] device tensor, dlogits, dvalues, dcvalues)."""

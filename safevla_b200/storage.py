@@ -159,8 +159,21 @@ class B200RolloutStorage:
             ops.gae_dual(self.costs_k[k], None, self.c_value_preds_k[k], None, self.masks, gamma, tau, gae_algo,
                          out=(self.c_returns_k[k], None, self.c_adv_targ_k[k], None))
         if normalize_advantage:
-            self.norm_adv_targ, _ = ops.normalize_advantage(self.adv_targ)
-            self.c_norm_adv_targ, _ = ops.normalize_advantage(self.c_adv_targ)
+            self.norm_adv_targ = self._normalized(self.adv_targ, kwargs.get("process_group"))
+            self.c_norm_adv_targ_k = torch.stack([self._normalized(self.c_adv_targ_k[k], kwargs.get("process_group"))
+                                                  for k in range(K)])  # each cost channel with its own statistics
+            self.c_norm_adv_targ = self.c_norm_adv_targ_k[0]
+
+    @staticmethod
+    def _normalized(adv: torch.Tensor, group=None) -> torch.Tensor:
+        """(adv - mean) / (std + 1e-5) with the statistics of the WHOLE batch: under data parallelism the three sums
+        {sum, sum of squares, count} are all-reduced first, so every rank normalises exactly as one process would."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            sums = ops.advantage_sums(adv)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            return ops.normalize_advantage_from_sums(adv, sums)[0]
+        return ops.normalize_advantage(adv)[0]
 
     def batched_experience_generator(self, num_mini_batch: int = 1) -> Iterator[Dict]:
         T, N = self.T, self.N

@@ -35,6 +35,7 @@ class PPOLagConfig:
     value_loss_coef: float = 0.5
     entropy_coef: float = 0.0
     use_clipped_value_loss: bool = False
+    normalize_advantage: bool = False  # :321 (off in the shipped config); global-batch statistics under data parallelism
     gamma: float = 0.99
     gae_lambda: float = 0.95
     update_repeats: int = 4
@@ -95,7 +96,11 @@ class PPOLagUpdater:
         assert K == self.lagrange.K == m.K, "storage, model and cost limits must agree on the number of cost channels"
         # the bootstrap rows (value / cost-value predictions of the step after the rollout) are already in the arena
         storage.before_updates(next_value=storage.value_preds[T], next_c_value=None,
-                               use_gae=True, gamma=c.gamma, tau=c.gae_lambda)
+                               use_gae=True, gamma=c.gamma, tau=c.gae_lambda,
+                               normalize_advantage=c.normalize_advantage, process_group=self.pg)
+        adv_t = storage.norm_adv_targ if c.normalize_advantage else storage.adv_targ
+        c_adv_1 = storage.c_norm_adv_targ if c.normalize_advantage else storage.c_adv_targ
+        c_adv_k = storage.c_norm_adv_targ_k if c.normalize_advantage else storage.c_adv_targ_k
         obs = {k: v[:T] for k, v in storage.observations.items()}
         rc = m.prepare(obs, T, N)
         pa = storage.prev_actions[:T]
@@ -133,11 +138,11 @@ class PPOLagUpdater:
                 m.tower_backward(COST, states[COST], None, dcv)
                 scal = torch.cat([scal[0:4], scal_c[4:5], scal[5:]])  # [0] value-critic total, [4] cost-critic total
             else:
-                c_adv, lam = storage.c_adv_targ, self.lagrange.lagrangian_multiplier
+                c_adv, lam = c_adv_1, self.lagrange.lagrangian_multiplier
                 if K > 1:  # fold the K (advantage, multiplier) pairs into the one pair the fused loss takes
-                    c_adv, lam = ops.combine_cost_advantages(storage.c_adv_targ_k.view(K, R), lam)
+                    c_adv, lam = ops.combine_cost_advantages(c_adv_k.reshape(K, R), lam)
                 scal, dl, dv, _ = ops.ppo_lag_fwd_bwd(
-                    outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, storage.adv_targ,
+                    outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, adv_t,
                     c_adv, outs[CRITIC]["values"], storage.returns[:T], None, None,
                     lam, hp, old_values=storage.value_preds[:T])
                 m.tower_backward(ACTOR, states[ACTOR], dl, None)

@@ -71,6 +71,23 @@ def test_gae_closed_form_and_mask_cut(dev):
     assert torch.allclose(ret2[9, :, 0].cpu(), torch.ones(N))
 
 
+def test_normalize_advantage_two_phase_matches_global_statistics(dev):
+    """Data-parallel form: per-shard {sum, sum^2, n} added up (what the all-reduce does), then every shard normalised
+    with the global mean / unbiased std -- equals normalising the concatenated batch in one call."""
+    g = torch.Generator().manual_seed(3)
+    full = (torch.randn(128, 12, 1, generator=g) * 3 + 0.7).to(dev)
+    ref, st_ref = _ops().normalize_advantage(full)
+    shards = [full[:, :5].contiguous(), full[:, 5:].contiguous()]
+    sums = sum(_ops().advantage_sums(s) for s in shards)
+    assert abs(sums[2].item() - full.numel()) == 0
+    outs = [_ops().normalize_advantage_from_sums(s, sums) for s in shards]
+    got = torch.cat([o[0] for o in outs], 1)
+    assert torch.allclose(got, ref, atol=2e-6, rtol=1e-5)
+    assert torch.allclose(outs[0][1], st_ref, atol=1e-6, rtol=1e-5)
+    exp = (full - full.mean()) / (full.std() + 1e-5)
+    assert torch.allclose(got, exp, atol=1e-5, rtol=1e-4)
+
+
 def test_normalize_advantage(dev):
     a = torch.randn(128, 64, 1) * 3 + 1
     out, stats = _ops().normalize_advantage(a.to(dev))

@@ -56,7 +56,7 @@ def _slice(ro, lo, hi):
     return out
 
 
-def _run(rank, world, port, out):
+def _run(rank, world, port, out, normalize=False):
     from safevla_b200.model import B200SafeActorCritic
     from safevla_b200.parallel import shard_samplers
     from safevla_b200.storage import B200RolloutStorage
@@ -71,7 +71,7 @@ def _run(rank, world, port, out):
     model = B200SafeActorCritic(A, C, precision="fp32", state_dict=sd, device=dev, extras="off")
     st = B200RolloutStorage(T, dev)
     st.load_rollout(_slice(ro, lo, hi), vp[:, lo:hi].contiguous(), cvp[:, lo:hi].contiguous(), logp[:, lo:hi].contiguous())
-    upd = PPOLagUpdater(model, PPOLagConfig(update_repeats=2, lr=1e-3, eps=1e-4))
+    upd = PPOLagUpdater(model, PPOLagConfig(update_repeats=2, lr=1e-3, eps=1e-4, normalize_advantage=normalize))
     res = upd.update(st)
     torch.cuda.synchronize()
     out[rank] = (model.param_arena.cpu(), res["lambda"].cpu(), res["grad_sq_norm"].cpu())
@@ -79,13 +79,15 @@ def _run(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_two_rank_update_equals_single_process_update():
+@pytest.mark.parametrize("normalize", [False, True])
+def test_two_rank_update_equals_single_process_update(normalize):
+    """normalize=True: advantage normalisation uses the all-reduced {sum, sum^2, n}, i.e. global-batch statistics."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     mgr = mp.Manager()
     one, two = mgr.dict(), mgr.dict()
-    mp.spawn(_run, args=(1, 0, one), nprocs=1, join=True)
-    mp.spawn(_run, args=(2, _free_port(), two), nprocs=2, join=True)
+    mp.spawn(_run, args=(1, 0, one, normalize), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, _free_port(), two, normalize), nprocs=2, join=True)
     p1, lam1, sq1 = one[0]
     (pa, lama, sqa), (pb, lamb, sqb) = two[0], two[1]
     assert torch.equal(pa, pb) and torch.equal(lama, lamb), "ranks diverged"  # identical without a broadcast
