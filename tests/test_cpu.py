@@ -381,3 +381,73 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "cfg2_64env_128step" and d["vs_baseline"] is None
+
+
+# ------------------------------------------------------------------ property tests of the restated (unpinned) pieces
+from hypothesis import given, settings, strategies as hst  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(T=hst.integers(1, 24), N=hst.integers(1, 4), seed=hst.integers(0, 10_000), p_done=hst.floats(0.0, 0.5),
+       gamma=hst.floats(0.5, 1.0), lam=hst.floats(0.0, 1.0))
+def test_gae_recursion_equals_explicit_double_sum(T, N, seed, p_done, gamma, lam):
+    """adv_t = sum_{k >= t} (gamma lam)^{k-t} (prod_{j=t+1..k} m_j) delta_k, evaluated directly in fp64, against the
+    sequential recursion the oracle (and the march kernel, bit for bit) runs."""
+    g = torch.Generator().manual_seed(seed)
+    r, v = torch.randn(T, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g)
+    m = (torch.rand(T + 1, N, 1, generator=g) >= p_done).float()
+    ret, adv = TO.gae_returns(r, v, m, gamma, lam)
+    rd, vd, md = r.double(), v.double(), m.double()
+    delta = rd + gamma * vd[1:] * md[1:] - vd[:-1]
+    exp = torch.zeros_like(rd)
+    for t in range(T):
+        w = torch.ones_like(rd[0])
+        for k in range(t, T):
+            if k > t:
+                w = w * gamma * lam * md[k]
+            exp[t] += w * delta[k]
+    assert torch.allclose(adv.double(), exp, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(ret[:T].double(), exp + vd[:-1], atol=2e-5, rtol=1e-5) and torch.equal(ret[T], v[T])
+    # lambda = 1 telescopes to the plain discounted return (`use_gae=False`)
+    ret1, _ = TO.gae_returns(r, v, m, gamma, 1.0)
+    ret_plain, _ = TO.gae_returns(r, v, m, gamma, 1.0, use_gae=False)
+    assert torch.allclose(ret1, ret_plain, atol=1e-4, rtol=1e-5)
+
+
+@settings(max_examples=25, deadline=None)
+@given(R=hst.integers(1, 40), A=hst.integers(2, 20), K=hst.integers(1, 4), seed=hst.integers(0, 10_000))
+def test_loss_identities_lambda_zero_and_channel_folding(R, A, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    logits, actions = torch.randn(R, 1, A, generator=g), torch.randint(0, A, (R, 1), generator=g)
+    old = torch.log_softmax(logits, -1).gather(-1, actions.unsqueeze(-1)).squeeze(-1) + 0.2 * torch.randn(R, 1, generator=g)
+    adv, vals, rets = (torch.randn(R, 1, 1, generator=g) for _ in range(3))
+    cadv = torch.randn(K, R, 1, 1, generator=g)
+    # lambda = 0: the cost advantage drops out (SafePPOLogGrad == PPOLogGrad, customized_loss.py:208-212 vs :350-362)
+    t0, _ = TO.safe_ppo_log_grad(logits, actions, old, adv, cadv[0], vals, rets, 0.0)
+    t1, _ = TO.safe_ppo_log_grad(logits, actions, old, adv, torch.zeros_like(adv), vals, rets, 0.0)
+    assert torch.equal(t0, t1)
+    # K channels: (A - sum_k l_k A_k) / (1 + sum_k l_k) == (A - L A_eff) / (1 + L) with the folded pair
+    lam = torch.rand(K, generator=g)
+    L = float(lam.sum())
+    eff = (lam.view(K, 1, 1, 1) * cadv).sum(0) / L if L > 0 else torch.zeros_like(adv)
+    direct = (adv - (lam.view(K, 1, 1, 1) * cadv).sum(0)) / (1.0 + L)
+    folded = (adv - L * eff) / (1.0 + L)
+    assert torch.allclose(direct, folded, atol=1e-6, rtol=1e-5)
+
+
+@settings(max_examples=20, deadline=None)
+@given(n0=hst.integers(1, 200), n1=hst.integers(1, 200), seed=hst.integers(0, 10_000))
+def test_two_phase_normalisation_identity(n0, n1, seed):
+    """{sum, sum^2, n} of the shards added up reproduce the statistics of the concatenated batch (what the data-parallel
+    advantage normalisation relies on)."""
+    g = torch.Generator().manual_seed(seed)
+    a, b = torch.randn(n0, generator=g) * 2 + 0.3, torch.randn(n1, generator=g) * 2 + 0.3
+    s = torch.stack([torch.stack([x.double().sum(), (x.double() ** 2).sum(), torch.tensor(float(x.numel()), dtype=torch.float64)])
+                     for x in (a, b)]).sum(0)
+    mean = s[0] / s[2]
+    var = (s[1] - s[2] * mean * mean) / (s[2] - 1) if s[2] > 1 else torch.tensor(0.0, dtype=torch.float64)
+    full = torch.cat([a, b])
+    exp = TO.normalize_advantage(full) if full.numel() > 1 else None
+    if exp is not None:
+        got = (full.double() - mean) / (var.clamp_min(0).sqrt() + 1e-5)
+        assert torch.allclose(got.float(), exp, atol=1e-4, rtol=1e-4)
