@@ -14,7 +14,6 @@ Deliberate, documented differences from the reference (results identical with dr
 """
 from __future__ import annotations
 
-from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 

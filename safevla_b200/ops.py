@@ -4,12 +4,12 @@ No function here computes anything with PyTorch ops -- torch only owns the memor
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 
 from . import _lib as L
-from ._lib import BF16, F32, IDENT, RowMap, check, dt, get_ctx, load_library, ptr, stream_ptr
+from ._lib import IDENT, check, dt, get_ctx, load_library, ptr, stream_ptr
 
 
 def _lib():

@@ -9,7 +9,7 @@ to the CPU oracle and (in the build container) to the reference code itself.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch

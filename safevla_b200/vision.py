@@ -26,7 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from ._lib import ATTN_FULL, EPI_GELU, EPI_NONE
+from ._lib import ATTN_FULL, EPI_GELU
 
 DINO_RGB_MEANS = (0.48145466, 0.4578275, 0.40821073)   # dino_preprocessors.py:42-43
 DINO_RGB_STDS = (0.26862954, 0.26130258, 0.27577711)
