@@ -30,6 +30,11 @@ CASES = {
     # two cameras + in-hand sensor, 20 actions, two samplers (S = 201)
     "T12_N2_A20_C2": dict(T=12, N=2, A=20, C=2, end_prob=1 / 5, wseed=12, rseed=4321, lam=0.05),
 }
+# Pinned on the CPU only (tests/test_cpu.py): the oracle at the BASELINE trajectory length -- a full 128-step decoder
+# window with several episode boundaries inside it (trajectory mask, time encoding, 20-action head)
+ORACLE_ONLY_CASES = {
+    "T128_N1_A20_C1": dict(T=128, N=1, A=20, C=1, end_prob=1 / 40, wseed=13, rseed=777, lam=0.2),
+}
 FULL_GRADS = ["actor.linear.weight", "actor.linear.bias", "critic_tsfm.critic.fc.weight",
               "visual_encoder.fusion_token", "last_actions_embed.weight",
               "critic_tsfm.visual_encoder.visual_sensor_token_raw_navigation_camera",
@@ -56,7 +61,10 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref_loss, _, _ = ref_shim.reference_modules()
-    for name, case in CASES.items():
+    only = set(sys.argv[1:])
+    for name, case in {**CASES, **ORACLE_ONLY_CASES}.items():
+        if only and name not in only:
+            continue
         T, N, A, C = case["T"], case["N"], case["A"], case["C"]
         sd = init_state_dict(A, C, case["wseed"], actor_gain=1.0)
         model = ref_shim.build_reference_model(A, C, seed=0, num_samplers=N)

@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from oracle import torch_oracle as TO  # noqa: E402
-from oracle.make_golden import CASES, GOLDEN_DIR, build_inputs  # noqa: E402
+from oracle.make_golden import CASES, GOLDEN_DIR, ORACLE_ONLY_CASES, build_inputs  # noqa: E402
 from safevla_b200.params import ParamLayout, T5Layout, init_state_dict, tower_spec  # noqa: E402
 from safevla_b200.synthetic import RolloutSpec, make_rollout, prev_actions_from  # noqa: E402
 
@@ -21,7 +21,7 @@ def relerr(a, b):
 
 
 # ------------------------------------------------------------------ oracle pinned on the reference's outputs
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + list(ORACLE_ONLY_CASES))
 def test_oracle_reproduces_reference_golden(name):
     torch.set_num_threads(os.cpu_count() or 1)
     gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
