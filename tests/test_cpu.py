@@ -451,3 +451,23 @@ def test_two_phase_normalisation_identity(n0, n1, seed):
     if exp is not None:
         got = (full.double() - mean) / (var.clamp_min(0).sqrt() + 1e-5)
         assert torch.allclose(got.float(), exp, atol=1e-4, rtol=1e-4)
+
+
+def test_gae_c_restatement_is_bit_identical():
+    """oracle/c/gae_ref.c (plain C, no FMA contraction) and oracle/torch_oracle.py::gae_returns produce the same bits:
+    two independent restatements of the recursion the CUDA march kernel is held to bit for bit."""
+    import ctypes as C
+    from oracle.c import build as oracle_c
+    lib = C.CDLL(oracle_c.build())
+    lib.gae_returns_f32.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_double, C.c_double]
+    lib.discounted_returns_f32.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_double]
+    g = torch.Generator().manual_seed(0)
+    for T, N, gamma, lam in ((128, 64, 0.99, 0.95), (1, 1, 0.9, 0.5), (37, 5, 0.97, 1.0), (16, 3, 1.0, 0.0)):
+        r, v = torch.randn(T, N, 1, generator=g) * 3, torch.randn(T + 1, N, 1, generator=g) * 3
+        m = (torch.rand(T + 1, N, 1, generator=g) > 0.1).float()
+        ret, adv = torch.empty_like(v), torch.empty_like(r)
+        lib.gae_returns_f32(r.data_ptr(), v.data_ptr(), m.data_ptr(), ret.data_ptr(), adv.data_ptr(), T, N, gamma, lam)
+        ret_t, adv_t = TO.gae_returns(r, v, m, gamma, lam)
+        assert torch.equal(ret, ret_t) and torch.equal(adv, adv_t), (T, N)
+        lib.discounted_returns_f32(r.data_ptr(), v.data_ptr(), m.data_ptr(), ret.data_ptr(), T, N, gamma)
+        assert torch.equal(ret, TO.gae_returns(r, v, m, gamma, lam, use_gae=False)[0])
