@@ -34,6 +34,31 @@ PATCH, DIM, HEADS, DEPTH, MLP = 14, 384, 6, 12, 1536
 LN_EPS = 1e-6
 
 
+def init_hub_state_dict(seed: int) -> Dict[str, torch.Tensor]:
+    """Seeded random weights in the torch.hub dinov2_vits14 layout (deterministic CPU generator) -- the synthetic
+    stand-in for the hub checkpoint that is not available offline; benchmarks, tools and the golden recipes use it."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=1.0: torch.randn(*s, generator=g) * std  # noqa: E731
+    sd = {"cls_token": rn(1, 1, DIM, std=0.5), "pos_embed": rn(1, 1 + 37 * 37, DIM, std=0.3),
+          "mask_token": torch.zeros(1, DIM),
+          "patch_embed.proj.weight": rn(DIM, 3, PATCH, PATCH, std=1.0 / math.sqrt(3 * PATCH * PATCH)),
+          "patch_embed.proj.bias": rn(DIM, std=0.1)}
+    for i in range(DEPTH):
+        q = f"blocks.{i}."
+        sd.update({
+            q + "norm1.weight": 1 + rn(DIM, std=0.1), q + "norm1.bias": rn(DIM, std=0.1),
+            q + "attn.qkv.weight": rn(3 * DIM, DIM, std=1.5 / math.sqrt(DIM)), q + "attn.qkv.bias": rn(3 * DIM, std=0.1),
+            q + "attn.proj.weight": rn(DIM, DIM, std=1.0 / math.sqrt(DIM)), q + "attn.proj.bias": rn(DIM, std=0.1),
+            q + "ls1.gamma": 0.5 + torch.rand(DIM, generator=g),
+            q + "norm2.weight": 1 + rn(DIM, std=0.1), q + "norm2.bias": rn(DIM, std=0.1),
+            q + "mlp.fc1.weight": rn(MLP, DIM, std=1.0 / math.sqrt(DIM)), q + "mlp.fc1.bias": rn(MLP, std=0.1),
+            q + "mlp.fc2.weight": rn(DIM, MLP, std=1.0 / math.sqrt(MLP)), q + "mlp.fc2.bias": rn(DIM, std=0.1),
+            q + "ls2.gamma": 0.5 + torch.rand(DIM, generator=g),
+        })
+    sd["norm.weight"], sd["norm.bias"] = 1 + rn(DIM, std=0.1), rn(DIM, std=0.1)
+    return sd
+
+
 def hub_to_canonical(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """facebookresearch/dinov2 (torch.hub) or HF Dinov2Model state dict -> one canonical layout."""
     sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in sd.items()}

@@ -3,11 +3,10 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vit_oracle as VO  # seeded weights only (tool, not product)
 from safevla_b200 import _lib as L
-from safevla_b200.vision import B200DinoViTPreprocessor
+from safevla_b200.vision import B200DinoViTPreprocessor, init_hub_state_dict
 dev = torch.device("cuda:0")
-pre = B200DinoViTPreprocessor("rgb", VO.init_hub_state_dict(0), precision="bf16", device=dev)
+pre = B200DinoViTPreprocessor("rgb", init_hub_state_dict(0), precision="bf16", device=dev)
 GF = 12 * (2 * 433 * 384 * (1152 + 384 + 2 * 1536) + 4 * 433 * 433 * 64 * 6) / 1e9 + 2 * 432 * 588 * 384 / 1e9
 for N in (8, 64, 256, 1024):
     fr = torch.randint(0, 256, (N, 224, 384, 3), dtype=torch.uint8, device=dev)
