@@ -108,7 +108,8 @@ struct TcArgs {
   float* asum;     // bias gradient fused into a weight-gradient launch (gemm_tc2.cu), or NULL
   float* asum_ws;  // its split-K partials
   int tma_store;
-  int dbg;  // SVLA_TC_DBG experiments: 1 = skip the epilogue entirely, 2 = TMEM loads only (no global stores)
+  int dbg;  // SVLA_TC_DBG experiments: 1 = skip the epilogue entirely, 2 = TMEM loads only (no global stores),
+            // 9 = 32-column chunks instead of the 64-column block epilogue (A/B switch used for the same-box comparison)
 };
 
 __device__ __forceinline__ float ld_elem(const void* p, int dt, long long i) {
