@@ -99,10 +99,12 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int, device: str = "cpu"):
+def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int, device: str = "cpu", tf32: bool = False,
+               autocast=None):
     """Times the oracle's whole update on a sampler-subsample (sample_N of the N samplers, first sample_T steps, ONE
-    update repeat); returns samples/s and a description.  device="cuda" runs the same torch-eager restatement on the
-    GPU (fp32, TF32 off): the stock-library baseline of SURVEY 8d, reported in DESIGN.md, never by the driver's arms."""
+    update repeat); returns samples/s, seconds per iteration and a description.  device="cuda" runs the same torch-eager
+    restatement on the GPU (fp32; optionally TF32 matmuls or bf16 autocast): the stock-library baseline of SURVEY 8d
+    (`library_baseline` in the JSON line)."""
     from oracle.update_oracle import oracle_update  # the one place bench.py executes oracle/
     from safevla_b200.params import init_state_dict
     from safevla_b200.synthetic import RolloutSpec, make_rollout
@@ -116,28 +118,45 @@ def cpu_sample(wl, steps: int, warmup: int, sample_T: int, sample_N: int, device
     cvp = torch.randn(sample_T + 1, sample_N, 1, generator=g).abs()
     logp = -3.0 + 0.05 * torch.randn(sample_T, sample_N, generator=g)
     cfg = PPOLagConfig(update_repeats=1)
-    if device != "cpu":
+    on_gpu = device != "cpu"
+    if on_gpu:
         def mv(x):
             if isinstance(x, dict):
                 return {k: mv(v) for k, v in x.items()}
             return x.to(device) if torch.is_tensor(x) else x
         sd, ro, vp, cvp, logp = mv(sd), mv(ro), vp.to(device), cvp.to(device), logp.to(device)
         torch.set_default_device(device)  # the restatement creates its index / mask tensors with bare factories
+    old_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = bool(tf32)
     times = []
-    for i in range(warmup + steps):
-        if device != "cpu":
-            torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        oracle_update(sd, ro, vp, cvp, logp, cfg, wl["A"], wl["C"])
-        if device != "cpu":
-            torch.cuda.synchronize()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    try:
+        for i in range(warmup + steps):
+            if on_gpu:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if autocast is not None:
+                with torch.autocast("cuda", dtype=autocast):
+                    oracle_update(sd, ro, vp, cvp, logp, cfg, wl["A"], wl["C"])
+            else:
+                oracle_update(sd, ro, vp, cvp, logp, cfg, wl["A"], wl["C"])
+            if on_gpu:
+                torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_tf32
+        if on_gpu:
+            torch.set_default_device("cpu")
     t = sum(times) / len(times)
-    what = (f"CPU oracle (torch eager fp32, {torch.get_num_threads()} threads)" if device == "cpu"
-            else "torch-eager oracle on the GPU (fp32)")
+    mode = "bf16 autocast" if autocast is not None else ("TF32 matmuls" if tf32 else "fp32")
+    what = (f"CPU oracle (torch eager fp32, {torch.get_num_threads()} threads)" if not on_gpu
+            else f"torch-eager oracle on the GPU ({mode})")
     return sample_T * sample_N / t, t, (f"{what}: {sample_N} of {wl['N']} samplers x {sample_T} of {wl['T']} steps, "
-                                        f"1 of {UPDATE_REPEATS} update repeats per step")
+                                        f"1 of {UPDATE_REPEATS} update repeats per step, {warmup} warm-up + {steps} "
+                                        f"timed iterations")
+
+
+REF_SAMPLERS = 4  # "4 of 64 samplers, full T" per reference-arm step
 
 
 def run_reference(args, wl, name):
@@ -145,14 +164,10 @@ def run_reference(args, wl, name):
     if rank != 0:
         return
     if args.ref_device != "cpu":  # stock-library baseline on the GPU: larger sample, same code
-        if args.ref_tf32:
-            torch.backends.cuda.matmul.allow_tf32 = True
-            torch.backends.cudnn.allow_tf32 = True
         v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=wl["T"], sample_N=min(wl["N"], args.ref_samplers),
-                                device=args.ref_device)
-        desc += " (TF32 matmuls)" if args.ref_tf32 else ""
+                                device=args.ref_device, tf32=args.ref_tf32)
     else:
-        v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=min(wl["T"], 32), sample_N=1)
+        v, t, desc = cpu_sample(wl, args.steps, args.warmup, sample_T=wl["T"], sample_N=min(wl["N"], REF_SAMPLERS))
     line = {"impl": "reference" if args.ref_device == "cpu" else "reference-eager-" + args.ref_device, "metric": "ppo_lagrangian_update_samples_per_sec", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -163,6 +178,21 @@ def run_reference(args, wl, name):
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def library_baseline(wl, samplers: int = 8):
+    """The same torch-eager restatement of the reference on the B200 through the stock libraries (cuBLAS / ATen
+    kernels, autograd): fp32, TF32 matmuls and bf16 autocast.  This is what the reference's own code would reach on
+    this GPU, i.e. the baseline the hand-written path has to beat; the CPU arm is the contract's reference arm."""
+    out = {}
+    for key, kw in (("fp32", {}), ("tf32", {"tf32": True}), ("bf16_autocast", {"autocast": torch.bfloat16})):
+        try:
+            v, t, desc = cpu_sample(wl, 2, 1, sample_T=wl["T"], sample_N=min(wl["N"], samplers), device="cuda", **kw)
+            out[key] = {"value": v, "unit": "samples/s", "ms_per_iteration": t * 1e3, "sample": desc}
+        except Exception as e:  # noqa: BLE001  (e.g. out of memory next to the timed model: reported, not fatal)
+            out[key] = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -192,7 +222,7 @@ def scan_roofline(dev, pk):
             fn()
             ev[i + 1].record()
         torch.cuda.synchronize()
-        return min(ev[i].elapsed_time(ev[i + 1]) for i in range(n)) * 1e-3
+        return sum(ev[i].elapsed_time(ev[i + 1]) for i in range(n)) / n * 1e-3  # MEAN launch duration
 
     t_gae = t_of(lambda: ops.gae_dual(r, c, v, vc, m, 0.99, 0.95, 1, out=out))
     lib, ctx = L.load_library(), L.get_ctx()
@@ -204,7 +234,7 @@ def scan_roofline(dev, pk):
                                          dv.data_ptr(), None, T * N, A, L.stream_ptr()))
     t_loss = t_of(loss)
     gae_b, loss_b = 36.0 * T * N, (8.0 * A + 44.0) * T * N
-    return {"shape": f"T={T},N={N},A={A}", "peak_gbs": pk["hbm"], "peak_src": pk["src"],
+    return {"shape": f"T={T},N={N},A={A}", "peak_gbs": pk["hbm"], "peak_src": pk["src"], "timing": "mean of 20 launches",
             "gae": {"gbs": gae_b / t_gae / 1e9, "frac": gae_b / t_gae / 1e9 / pk["hbm"], "us": t_gae * 1e6},
             "loss": {"gbs": loss_b / t_loss / 1e9, "frac": loss_b / t_loss / 1e9 / pk["hbm"], "us": t_loss * 1e6}}
 
@@ -224,7 +254,9 @@ def run_b200(args, wl, name):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # any NCCL_DEBUG level prints a version banner on stdout; keep it to the JSON line
+        # NCCL_DEBUG is left as the caller set it (the driver counts ranks from NCCL's INFO lines); NCCL would print
+        # them on stdout, which must carry only the JSON line, so they are routed to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert wl["N"] % world == 0, "samplers must divide evenly over the ranks"
     T, A, C = wl["T"], wl["A"], wl["C"]
@@ -333,10 +365,25 @@ def run_b200(args, wl, name):
 
     samples = T * wl["N"] * UPDATE_REPEATS
     value, e2e = samples / t_res, samples / t_e2e
+    dtype_name = {"bf16": "bf16", "fp32": "f32", "bf16x3": "f32 (3 split-bf16 tcgen05 products per GEMM)",
+                  "bf16x6": "f32 (6 split-bf16 tcgen05 products per GEMM)"}[args.precision]
     # roofline of the dominant kernel: summed algorithmic FLOPs / summed event time of its launches
     roof = None
+    executed = None
     if prof:
-        best = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        # FLOPs the step really launches (every GEMM's 2MNK + the attention kernels' S x S x dh products), next to
+        # the SURVEY model's algorithmic figure (which also counts work the CLS-only last layer and the prompt
+        # de-duplication legitimately skip)
+        ex_flops = sum(r["flops"] for r in prof.values()) / args.steps
+        ex_tf = ex_flops / t_res / 1e12
+        executed = {"achieved": ex_tf * world, "peak": pk["tf_sust"] * world, "frac": ex_tf / pk["tf_sust"],
+                    "gflop_per_sample": ex_flops * world / samples / 1e9,
+                    "by_kernel": {k: {"tflop_per_step": r["flops"] / args.steps / 1e12,
+                                      "ms_per_step": r["ms"] / args.steps, "launches_per_step": r["n"] // args.steps,
+                                      "tflops": r["flops"] / max(r["ms"], 1e-9) / 1e9}
+                                  for k, r in sorted(prof.items())},
+                    "note": "rank 0's launched FLOPs (GEMM 2MNK incl. split-operand products + attention) / step time"}
+        best = max(((k, v) for k, v in prof.items() if "gemm" in k), key=lambda kv: kv[1]["ms"])
         kname, rec = best
         torch.cuda.synchronize()
         ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
@@ -350,7 +397,7 @@ def run_b200(args, wl, name):
         "metric": "ppo_lagrangian_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": dtype_name, "data": "synthetic",
         "config": {"workload": name, "T": T, "N_global": wl["N"], "N_per_rank": n_local, "actions": A, "cameras": C,
                    "prompt_tokens": wl["L"], "cost_channels": K, "update_repeats": UPDATE_REPEATS,
                    "parallelism": f"dp{world}",
@@ -364,13 +411,18 @@ def run_b200(args, wl, name):
         "step_algorithmic_tflops": {"achieved": step_tf, "peak": pk["tf_sust"] * world,
                                     "frac": step_tf / (pk["tf_sust"] * world), "gflop_per_sample": wl["gflop_per_sample"],
                                     "note": "SURVEY 8a FLOP model x samples/s over all GPUs; includes every non-GEMM kernel"},
+        "step_executed_tflops": executed,
     }
     if world == 1:
         line["roofline_scan"] = scan
         if not args.no_cpu_baseline:
-            v, t, desc = cpu_sample(wl, 1, 0, sample_T=min(T, 32), sample_N=1)
+            v, t, desc = cpu_sample(wl, 1, 1, sample_T=T, sample_N=min(wl["N"], 2))  # warmed: 1 + 1 iterations
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": desc}
+        if not args.no_library_baseline:
+            del upd, storage, model  # the eager baseline needs the HBM the stash held
+            torch.cuda.empty_cache()
+            line["library_baseline"] = library_baseline(wl)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -383,9 +435,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_64env_128step", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "bf16x6"])
     ap.add_argument("--chunk-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", help="--impl reference only: cpu (the reference arm) or cuda")
     ap.add_argument("--ref-samplers", type=int, default=2, help="--ref-device cuda: samplers in the timed sample")
     ap.add_argument("--ref-tf32", action="store_true", help="--ref-device cuda: allow TF32 tensor-core matmuls")

@@ -66,6 +66,13 @@ int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* costs, const
                   float* adv, float* c_adv, int T, int N, double gamma, double lam, int algo,
                   svla_stream stream);
 
+/* The `use_gae = False` branch of the same `compute_returns` (not used by the shipped config, kept
+ * for API completeness): ret_T = V_T, ret_t = ret_{t+1} * gamma * m_{t+1} + r_t, adv_t = ret_t - V_t, on both
+ * streams in one launch; same shapes as svla_gae_dual, bit-exact with the sequential loop. */
+int svla_discounted_returns_dual(svla_ctx* ctx, const float* rewards, const float* costs, const float* value_preds,
+                                 const float* c_value_preds, const float* masks, float* returns, float* c_returns,
+                                 float* adv, float* c_adv, int T, int N, double gamma, svla_stream stream);
+
 /* mean / unbiased std of adv over all T*N elements -> stats[0..1] (device), then
  * norm_adv = (adv - mean) / (std + 1e-5)  (allenact `norm_adv_targ`; unused by the shipped
  * config: normalize_advantage=False, training/online/dinov2_vits_tsfm_base.py:321). */
@@ -94,7 +101,9 @@ typedef struct {
 #define SVLA_PPO_NSCALARS 16
 /* out_scalars (device, float[16]): 0 total, 1 value_loss, 2 action_loss(mean), 3 entropy term
  * (= mean(-H), the sign the reference logs, :401), 4 cvalue_loss, 5 approx KL(old||new),
- * 6 clip fraction, 7 mean ratio, 8 penalty (lambda used), 9 sum adv_hat, 10..15 reserved. */
+ * 6 clip fraction, 7 mean ratio, 8 penalty (lambda used), 9 sum adv_hat, 10 number of rows whose action index was
+ * outside [0, A) (such rows are evaluated with the index clamped; callers treat a non-zero count as an error),
+ * 11..15 reserved. */
 
 /* Fused SafePPOLogGrad / PPOLogGrad / PPOValue / SafePPOValue forward AND backward
  * (customized_loss.py:317-449, :178-298).  logits [R,A] fp32; actions int64
@@ -294,6 +303,18 @@ int svla_scale_by(svla_ctx* ctx, float* x, long long n, const float* scale_dev, 
 
 /* fp32 -> bf16 cast of a flat buffer (parameter shadow) */
 int svla_cast_bf16(svla_ctx* ctx, const float* x, void* y, long long n, svla_stream stream);
+
+/* Split-operand staging of the parity-grade tensor-core mode (precision "bf16x3" / "bf16x6"): x fp32 [rows, cols]
+ * (row stride ldx) is decomposed into bf16 parts p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) and the parts
+ * named by pattern[0..nprod) are concatenated along the contraction dimension of the GEMM operand the tensor will be:
+ *   axis = 1: out[r, j * cols + c] = part_{pattern[j]}(x[r, c])      (K-major operand, out [rows, nprod * cols])
+ *   axis = 0: out[j * rows + r, c] = part_{pattern[j]}(x[r, c])      (MN-major operand, out [nprod * rows, cols])
+ * With A staged by (0,1,0) and B by (0,0,1) ONE svla_gemm launch on the bf16 tcgen05 kernels accumulates
+ * p0 q0 + p1 q0 + p0 q1 in fp32 -- the fp32 product to ~2^-16 relative (six products with three parts: ~2^-23).
+ * Replaces nothing in the reference (which multiplies in fp32 on the CPU/GPU library path): it is how BASELINE's
+ * "within 1e-4 rel fp32" gate is met on the tensor cores. */
+int svla_split_concat(svla_ctx* ctx, const float* x, long long ldx, long long rows, int cols, void* out, long long ldo,
+                      int axis, int nprod, const int* pattern, svla_stream stream);
 
 /* 64-bit hash of each goal-byte row (uint8 [R, L]) for prompt de-duplication; replaces the per-row
  * CPU decode loop at allenact_dino_transformer.py:591-598. */

@@ -68,7 +68,8 @@ def oracle_update(sd: Dict[str, torch.Tensor], ro: Dict, value_preds, c_value_pr
         for k, g in zip(with_grad, grads):
             params[k], m[k], v[k] = TO.adam_step(params[k], g, m[k], v[k], step, cfg.lr, cfg.betas[0], cfg.betas[1],
                                                  cfg.eps)
-    cnt = max(float(ro["episode_count"]), 1.0)
+    cnt = float(ro["episode_count"])
     sums = ro["episode_cost_sum"].reshape(-1).tolist()
-    lams = [l.update(sums[k] / cnt) for k, l in enumerate(lags)]
+    # no finished episode in the rollout -> no Jc estimate: the multiplier and its Adam state are left untouched
+    lams = [(l.update(sums[k] / cnt) if cnt >= 1.0 else l.lam) for k, l in enumerate(lags)]
     return params, (lams[0] if K == 1 else lams), info

@@ -64,6 +64,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_sm_count": [c_p],
     "svla_launch_count": [],
     "svla_gae_dual": [c_p] + [c_p] * 9 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_p],
+    "svla_discounted_returns_dual": [c_p] + [c_p] * 9 + [C.c_int, C.c_int, C.c_double, c_p],
     "svla_normalize_advantage": [c_p, c_p, c_p, c_p, c_ll, c_p],
     "svla_advantage_sums": [c_p, c_p, c_ll, c_p, c_p],
     "svla_normalize_advantage_from_sums": [c_p, c_p, c_p, c_p, c_p, c_ll, c_p],
@@ -106,6 +107,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_fill_rows": [c_p, c_p, c_p, C.c_int, c_ll, RowMap, c_ll, C.c_int, c_p],
     "svla_scale_by": [c_p, c_p, c_ll, c_p, c_p],
     "svla_cast_bf16": [c_p, c_p, c_p, c_ll, c_p],
+    "svla_split_concat": [c_p, c_p, c_ll, c_ll, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.POINTER(C.c_int), c_p],
     "svla_hash_rows": [c_p, c_p, c_ll, C.c_int, c_p, c_p],
     "svla_episode_cost_step": [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p],
     "svla_combine_cost_advantages": [c_p, c_p, c_p, C.c_int, c_ll, c_p, c_p, c_p],

@@ -357,6 +357,51 @@ __global__ void __launch_bounds__(256) adv_normalize(const float* x, float* y, l
     y[i] = (x[i] - mean) * inv;
 }
 
+
+// ---- use_gae = False: plain discounted returns --------------------------------------------------------------
+//   ret_T = V_T ;  ret_t = (ret_{t+1} * gamma) * m_{t+1} + r_t ;  adv_t = ret_t - V_t
+// (upstream allenact RolloutBlockStorage.compute_returns, the `else` branch).  Lanes = samplers
+// (coalesced rows), blockIdx.y = stream; each thread pulls a 16-step chunk of r / m / V into registers (all loads
+// in flight at once), then runs the dependent chain: three roundings per step in the recursion's own order, no FMA.
+constexpr int kDL = 16;
+__global__ void __launch_bounds__(128) discounted_returns_kernel(GaeArgs a) {
+  const int s = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  const float* r = a.r[s];
+  const float* v = a.v[s];
+  float* ret = a.ret[s];
+  float* adv = a.adv[s];
+  const int T = a.T, N = a.N;
+  float g = v[(size_t)T * N + n];
+  ret[(size_t)T * N + n] = g;
+  for (int t1 = T; t1 > 0; t1 -= kDL) {
+    const int t0 = max(0, t1 - kDL), cnt = t1 - t0;
+    float rr[kDL], mm[kDL], vv[kDL];
+#pragma unroll
+    for (int j = 0; j < kDL; ++j)
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+        rr[j] = __ldg(r + off);
+        mm[j] = __ldg(a.m + off + N);
+        vv[j] = __ldg(v + off);
+      }
+#pragma unroll
+    for (int j = kDL - 1; j >= 0; --j)
+      if (j < cnt) {
+        g = __fadd_rn(__fmul_rn(__fmul_rn(g, a.gamma), mm[j]), rr[j]);
+        rr[j] = g;
+      }
+#pragma unroll
+    for (int j = 0; j < kDL; ++j)
+      if (j < cnt) {
+        const size_t off = (size_t)(t0 + j) * N + n;
+        ret[off] = rr[j];
+        adv[off] = __fsub_rn(rr[j], vv[j]);
+      }
+  }
+}
+
 template <int kL, int kW, int kNW>
 void launch_march(const GaeArgs& a, cudaStream_t st) {
   gae_march_kernel<kL, kW, kNW><<<(a.N + 32 * kNW - 1) / (32 * kNW), 32 * kW * kNW, 0, st>>>(a);
@@ -445,6 +490,30 @@ extern "C" int svla_gae_dual(svla_ctx* ctx, const float* rewards, const float* c
     svla_set_error("svla_gae_dual: bad algo %d", algo);
     return SVLA_ERR_BAD_ARG;
   }
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
+extern "C" int svla_discounted_returns_dual(svla_ctx* ctx, const float* rewards, const float* costs,
+                                            const float* value_preds, const float* c_value_preds, const float* masks,
+                                            float* returns, float* c_returns, float* adv, float* c_adv, int T, int N,
+                                            double gamma, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx, "ctx is NULL");
+  SVLA_CHECK_ARG(T >= 0 && N >= 0, "negative shape");
+  SVLA_CHECK_ARG(rewards && value_preds && masks && returns && adv, "NULL reward-stream buffer");
+  if (N == 0) return SVLA_OK;
+  GaeArgs a;
+  a.r[0] = rewards; a.v[0] = value_preds; a.ret[0] = returns; a.adv[0] = adv;
+  a.r[1] = costs; a.v[1] = c_value_preds; a.ret[1] = c_returns; a.adv[1] = c_adv;
+  a.ns = 1;
+  if (costs) {
+    SVLA_CHECK_ARG(c_value_preds && c_returns && c_adv, "NULL cost-stream buffer");
+    a.ns = 2;
+  }
+  a.m = masks; a.T = T; a.N = N;
+  a.gamma = (float)gamma;
+  a.gl = 0.f;
+  discounted_returns_kernel<<<dim3((N + 127) / 128, a.ns), 128, 0, as_stream(stream)>>>(a);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }

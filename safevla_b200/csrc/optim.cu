@@ -80,7 +80,10 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
 __global__ void lagrange_kernel(float* lam, float* st, const float* cost_sum_cnt, float limit, float lr, float ub) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float cnt = cost_sum_cnt[1];
-  const float jc = cost_sum_cnt[0] / fmaxf(cnt, 1.f);
+  // a rollout in which no episode finished carries no episode-cost information: lambda and its Adam state stay
+  // untouched (treating it as Jc = 0 would push lambda towards 0 and weaken the constraint); st[3] keeps the last Jc
+  if (!(cnt >= 1.f)) return;
+  const float jc = cost_sum_cnt[0] / cnt;
   const float g = -(jc - limit);  // d/dlambda of -lambda * (Jc - d)
   float m = st[0], v = st[1];
   const float t = st[2] + 1.f;

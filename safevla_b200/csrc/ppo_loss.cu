@@ -86,7 +86,8 @@ __device__ __forceinline__ void finish_reduction(const PpoArgs& a, float* acc, f
       a.out[7] = tot[6] * ic;
       a.out[8] = pen;
       a.out[9] = tot[7];
-      for (int j = 10; j < SVLA_PPO_NSCALARS; ++j) a.out[j] = 0.f;
+      a.out[10] = tot[8];  // number of rows whose action index was outside [0, A)
+      for (int j = 11; j < SVLA_PPO_NSCALARS; ++j) a.out[j] = 0.f;
       *a.ticket = 0u;
     }
   }
@@ -141,7 +142,11 @@ __global__ void __launch_bounds__(kRows) ppo_lag_kernel(PpoArgs a) {
         float* row = tile + tid * ldt;
         float mx = -INFINITY;
         for (int k = 0; k < A; ++k) mx = fmaxf(mx, row[k]);
-        const int act = (int)a.actions[i];
+        int act = (int)a.actions[i];
+        if (act < 0 || act >= A) {  // corrupted / mis-shaped actions: counted (out[10]) and clamped, never read out of range
+          acc[8] += 1.f;
+          act = min(max(act, 0), A - 1);
+        }
         const float l_act = row[act] - mx;
         // one exp per logit: e_k overwrites the tile; H = log(se) - sum(e_k (l_k - mx)) / se
         float se = 0.f, sel = 0.f;
@@ -301,7 +306,11 @@ __global__ void __launch_bounds__(256, 2) ppo_lag_vec_kernel(PpoArgs a) {
     }
     if (wt + stride < ntiles) fetch(wt + stride);  // next tile's loads fly during this tile's arithmetic
     if (live) {
-      const int act = c.act;
+      int act = c.act;
+      if (act < 0 || act >= A) {  // counted (out[10]) and clamped, same rule as ppo_lag_kernel
+        acc[8] += 1.f;
+        act = min(max(act, 0), A - 1);
+      }
       float mx = -INFINITY;
 #pragma unroll
       for (int k = 0; k < A; ++k) mx = fmaxf(mx, row[k]);

@@ -34,10 +34,12 @@ class _FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        # the saved gradient buffers stay d loss / d input: a second backward through this node (retain_graph, the
+        # loss used in two sums) must not compound the upstream scale, so the scaling happens on a copy
         scale = grad_out.reshape(1).to(torch.float32).contiguous()
         outs = []
         for g in ctx.grads:
-            outs.append(None if g is None else ops.scale_by(g, scale))
+            outs.append(None if g is None else ops.scale_by(g.clone(), scale))
         return (None, None, *outs)
 
 
@@ -60,6 +62,9 @@ def fused_ppo_loss(*, logits, values, c_values, batch, hp: L.PpoHparams, lagrang
     c_adv = g(c_adv_key) if (logits is not None and hp.use_lagrangian) else None
     if lam is not None and lam.numel() > 1 and c_adv is not None:
         # K cost channels (extension): c_adv is channel-major [K, T, N, 1]; fold (A_c,k, lambda_k) into one pair
+        R = logits.numel() // logits.shape[-1]
+        assert c_adv.numel() == lam.numel() * R, \
+            f"cost advantages must be channel-major [K={lam.numel()}, T, N, 1] ({lam.numel() * R} values), got {tuple(c_adv.shape)}"
         c_adv, lam = ops.combine_cost_advantages(c_adv.view(lam.numel(), -1), lam)
     scal, dlogits, dvalues, dcvalues = ops.ppo_lag_fwd_bwd(
         _flat(logits.detach()) if logits is not None else None, actions,
@@ -119,6 +124,9 @@ class _LogGradBase(PPO):
         total, scal = fused_ppo_loss(logits=logits, values=values, c_values=None, batch=batch, hp=hp,
                                      lagrangian_multiplier=lm, adv_key=self.adv_key, c_adv_key=self.c_adv_key)
         s = scal.tolist()  # the one host sync of this loss
+        if s[10] != 0.0:
+            raise ValueError(f"{int(s[10])} action indices outside [0, {logits.shape[-1]}): batch['actions'] is corrupted "
+                             "or mis-shaped")
         ex = actor_critic_output.extras
         info = {
             "ppo_total": s[0], "value": s[1], "action": s[2], "entropy": s[3],
@@ -153,8 +161,17 @@ class PPOValue(AbstractActorCriticLoss):
 
     def loss(self, step_count: int, batch: Dict, actor_critic_output, *args, **kwargs):
         v = actor_critic_output.c_values if self._cost else actor_critic_output.values
+        K = v.shape[-1] if self._cost else 1
+        R = v.numel() // K
+        if K > 1:
+            # K cost channels (extension): the head emits [T, N, K] row-major while the storage keeps the targets
+            # channel-major [K, T, N, 1]; pair them as [R, K] and sum the per-channel means (1 / R), exactly as
+            # PPOLagUpdater's stage-0 path does
+            tnk = lambda x: x.to(v.device).reshape(K, R).t().contiguous()  # noqa: E731
+            batch = dict(batch, c_returns=tnk(batch["c_returns"]),
+                         c_values=tnk(batch["c_values"]) if batch.get("c_values") is not None else None)
         hp = L.PpoHparams(self.clip_param * self.clip_decay(step_count), 0.0, 0.0 if self._cost else 1.0, 0.0,
-                          1.0 if self._cost else 0.0, 1.0 / v.numel(), 1.0, int(self.use_clipped_value_loss), 0)
+                          1.0 if self._cost else 0.0, 1.0 / R, 1.0, int(self.use_clipped_value_loss), 0)
         total, scal = fused_ppo_loss(logits=None, values=None if self._cost else v, c_values=v if self._cost else None,
                                      batch=batch, hp=hp)
         return total, {"value": scal[4 if self._cost else 1].item()}

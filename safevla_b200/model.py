@@ -93,7 +93,11 @@ class B200SafeActorCritic(nn.Module):
                  time_step_uuid: str = "time_step", traj_idx_uuid: str = "traj_index", extras: str = "eager",
                  verify_dedupe: bool = True, max_steps: int = 1000, num_cost_channels: int = 1):
         super().__init__()
-        assert precision in ("bf16", "fp32")
+        # "bf16": bf16 operands on the tcgen05 kernels (the fast path); "fp32": fp32 FMA kernels (CUDA cores);
+        # "bf16x3" / "bf16x6": fp32 activations and weights, every tensor-core-shaped product evaluated on the tcgen05
+        # kernels as 3 / 6 split-bf16 products (parity-grade tensor-core mode, see csrc/split.cu)
+        assert precision in ("bf16", "fp32", "bf16x3", "bf16x6")
+        self.split = {"bf16x3": 3, "bf16x6": 6}.get(precision, 0)
         if not torch.cuda.is_available():
             raise RuntimeError("B200SafeActorCritic needs a CUDA device (sm_100a); there is no CPU fallback")
         self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -121,11 +125,13 @@ class B200SafeActorCritic(nn.Module):
         self.load_state_dict(state_dict if state_dict is not None
                              else init_state_dict(num_actions, num_cameras, seed, num_cost_channels=self.K), strict=True)
 
-        self.t5 = T5Encoder(self.t5_layout, self.t5_arena, self.adt)
+        self.t5 = T5Encoder(self.t5_layout, self.t5_arena, self.adt, self.split)
+        if self.split:
+            ops.split_cache_open()
         self.towers: List[Tower] = []
         for pre in TOWERS:
             tw = Tower(TowerWeights(self.layout, pre, self.param_arena, self.grad_arena, self.shadow_arena),
-                       num_actions, num_cameras, self.adt, cls_only_last_layer)
+                       num_actions, num_cameras, self.adt, cls_only_last_layer, self.split)
             tw.div_term = self.get_buffer(pre + "time_encoder.div_term")
             self.towers.append(tw)
         self._anchor = torch.zeros(1, device=self.dev, requires_grad=True)
@@ -177,6 +183,7 @@ class B200SafeActorCritic(nn.Module):
 
     def refresh_shadow(self):
         """bf16 GEMM-operand copy of the fp32 master weights (refreshed by the fused Adam kernel)."""
+        ops.split_cache_clear()  # staged split-operand copies of the weights are stale too
         if self.shadow_arena is not None:
             ops.cast_bf16(self.param_arena, self.shadow_arena)
         if getattr(self, "t5", None) is not None:  # frozen T5: bf16 operand copy + relative-position bias table
@@ -227,7 +234,10 @@ class B200SafeActorCritic(nn.Module):
     def prepare(self, observations: Dict[str, torch.Tensor], T: int, N: int) -> RolloutContext:
         rgb = observations[self.uu["rgb"]]
         goal = observations[self.uu["goal"]]
-        key = (rgb.data_ptr(), rgb._version, goal.data_ptr(), goal._version, T, N)
+        # every consumed observation tensor takes part (an in-place change of time_step / traj_index / the manipulation
+        # frames / in_hand alone must not reuse a stale context)
+        key = tuple((k, v.data_ptr(), v._version) for k, v in sorted(observations.items())
+                    if k in self.uu.values()) + (T, N)
         if self._ctx_cache is not None and self._ctx_cache.key == key:
             return self._ctx_cache
         R = T * N
@@ -341,6 +351,7 @@ class B200SafeActorCritic(nn.Module):
         T, N = prev_actions.shape
         if T == 1:
             return self._forward_step(observations, memory, prev_actions, masks)
+        ops.split_cache_clear()  # the weights may have been stepped by any optimizer since the last call
         rc = self.prepare({k: v[:T] for k, v in observations.items()}, T, N)
         pa = prev_actions.to(self.dev).contiguous()
         mk = masks.to(self.dev, dtype=torch.float32).reshape(T, N).contiguous()

@@ -44,6 +44,24 @@ def gae_dual(rewards, costs, value_preds, c_value_preds, masks, gamma: float, la
     return returns, c_returns, adv, c_adv
 
 
+def discounted_returns_dual(rewards, costs, value_preds, c_value_preds, masks, gamma: float, out=None):
+    """`use_gae=False`: ret_t = ret_{t+1} * gamma * m_{t+1} + r_t on both streams; same shapes / outputs as gae_dual."""
+    _cuda(rewards, costs, value_preds, c_value_preds, masks)
+    T = rewards.shape[0]
+    N = rewards[0].numel()
+    assert value_preds.shape[0] == T + 1 and masks.shape[0] == T + 1
+    if out is None:
+        returns, adv = torch.empty_like(value_preds), torch.empty_like(rewards)
+        c_returns = torch.empty_like(c_value_preds) if costs is not None else None
+        c_adv = torch.empty_like(costs) if costs is not None else None
+    else:
+        returns, c_returns, adv, c_adv = out
+    check(_lib().svla_discounted_returns_dual(get_ctx(), ptr(rewards), ptr(costs), ptr(value_preds), ptr(c_value_preds),
+                                              ptr(masks), ptr(returns), ptr(c_returns), ptr(adv), ptr(c_adv), T, N,
+                                              float(gamma), stream_ptr()), "svla_discounted_returns_dual")
+    return returns, c_returns, adv, c_adv
+
+
 def normalize_advantage(adv: torch.Tensor):
     _cuda(adv)
     out = torch.empty_like(adv)
@@ -151,11 +169,52 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 
 # ---- dense path --------------------------------------------------------------------------------
+# split-operand products (svla_split_concat): (parts of A, parts of B) per product, most significant first
+SPLIT_PATTERNS = {3: ((0, 1, 0), (0, 0, 1)), 6: ((0, 0, 1, 1, 0, 2), (0, 1, 0, 1, 2, 0))}
+_SPLIT_CACHE = None  # {key: staged operand} while a weight epoch is open (see split_cache_open)
+
+
+def split_concat(x: torch.Tensor, ldx: int, rows: int, cols: int, axis: int, pattern) -> torch.Tensor:
+    """fp32 [rows, cols] view (row stride ldx) -> bf16 operand with the parts `pattern` concatenated along the
+    contraction dimension: [rows, P * cols] (axis 1) or [P * rows, cols] (axis 0)."""
+    P = len(pattern)
+    out = torch.empty((rows, P * cols) if axis == 1 else (P * rows, cols), device=x.device, dtype=torch.bfloat16)
+    pat = (C.c_int * P)(*pattern)
+    check(_lib().svla_split_concat(get_ctx(), ptr(x), ldx, rows, cols, ptr(out), out.stride(0), axis, P, pat,
+                                   stream_ptr()), "svla_split_concat")
+    return out
+
+
+def split_cache_open():
+    """Staged copies of tensors flagged `cache_b` (weights) are reused until split_cache_clear(): a weight is split
+    once per optimizer step and operand layout instead of once per launch."""
+    global _SPLIT_CACHE
+    if _SPLIT_CACHE is None:
+        _SPLIT_CACHE = {}
+
+
+def split_cache_clear():
+    if _SPLIT_CACHE is not None:
+        _SPLIT_CACHE.clear()
+
+
+def _split_ok(M, N, K, P, trans_a, trans_b, lda, ldb):
+    """Shapes the tcgen05 kernels take (gemm_tc.cu: svla_gemm_tc_supported) once the operands are staged."""
+    if M < 64 or N < 64 or N % 64 or K < 64 or K % 4:
+        return False
+    if (trans_a and M % 8) or (not trans_a and (P * K) % 8) or (not trans_b and N % 8):
+        return False
+    return lda % 4 == 0 and ldb % 4 == 0
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, trans_b=True, bias=None,
          residual=None, aux=None, epilogue=L.EPI_NONE, accumulate=False, alpha=1.0, impl=0,
-         M=None, N=None, K=None, lda=None, ldb=None, ldc=None, colsum_a=None):
+         M=None, N=None, K=None, lda=None, ldb=None, ldc=None, colsum_a=None, split=0, cache_b=False):
     """out[M,N] = epi(alpha * op(a) op(b) + bias) [+ residual].  a/b/out are 2-D views whose last
-    dim is contiguous (row stride = leading dimension).  trans_b=True is the nn.Linear layout."""
+    dim is contiguous (row stride = leading dimension).  trans_b=True is the nn.Linear layout.
+    split = 3 / 6 (fp32 operands only): the product runs on the bf16 tcgen05 kernels as a sum of 3 / 6 split-operand
+    products in one launch (parity-grade tensor-core mode); shapes the tensor-core kernels do not take stay on the
+    fp32 FMA kernel."""
     for t in (a, b, out, residual, aux):
         if t is not None:
             assert t.is_cuda and t.stride(-1) == 1 and t.dim() == 2
@@ -171,6 +230,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     kb = b.shape[1] if trans_b else b.shape[0]
     assert kb == K, f"inner dims differ: {K} vs {kb}"
     assert out.shape[0] >= M and out.shape[1] >= N
+    if split and a.dtype == torch.float32 and b.dtype == torch.float32 and not (trans_a and trans_b) \
+            and _split_ok(M, N, K, len(SPLIT_PATTERNS[split][0]), trans_a, trans_b, lda, ldb):
+        pa, pb = SPLIT_PATTERNS[split]
+        a2 = split_concat(a, lda, K, M, 0, pa) if trans_a else split_concat(a, lda, M, K, 1, pa)
+        key = (b.data_ptr(), ldb, N, K, trans_b, split)
+        b2 = _SPLIT_CACHE.get(key) if (cache_b and _SPLIT_CACHE is not None) else None
+        if b2 is None:
+            b2 = split_concat(b, ldb, N, K, 1, pb) if trans_b else split_concat(b, ldb, K, N, 0, pb)
+            if cache_b and _SPLIT_CACHE is not None:
+                _SPLIT_CACHE[key] = b2
+        if colsum_a is not None:  # the staged operand holds every part more than once: sum the fp32 tensor itself
+            assert trans_a
+            colsum(a[:K, :M], colsum_a, accumulate=True)
+        return gemm(a2, b2, out, trans_a=trans_a, trans_b=trans_b, bias=bias, residual=residual, aux=aux,
+                    epilogue=epilogue, accumulate=accumulate, alpha=alpha, impl=impl, M=M, N=N, ldc=ldc)
     d = L.GemmDesc()
     d.M, d.N, d.K = M, N, K
     d.A, d.lda, d.transA = ptr(a), lda, int(trans_a)
@@ -192,14 +266,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
         check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
         return out
     # bench.py: CUDA-event timing of every GEMM launch on the launching stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     which = "svla_gemm_tc_kernel" if _lib().svla_gemm_which(C.byref(d)) == 2 else "gemm_simt_kernel"
-    e0.record()
-    check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
-    e1.record()
-    PROFILE.setdefault(which, []).append((2.0 * M * N * K, e0, e1, (M, N, K, int(trans_a), int(trans_b), epilogue,
-                                                                    int(accumulate), str(a.dtype)[6:], str(out.dtype)[6:],
-                                                                    residual is not None, colsum_a is not None)))
+    _timed(which, 2.0 * M * N * K, (M, N, K, int(trans_a), int(trans_b), epilogue, int(accumulate), str(a.dtype)[6:],
+                                    str(out.dtype)[6:], residual is not None, colsum_a is not None),
+           lambda: check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm"))
     return out
 
 
@@ -254,21 +324,36 @@ def rmsnorm_bwd(dy, x, w, rstd, dx, dw, accumulate_dx=False):
     return dx
 
 
+def _timed(which: str, flops: float, meta, launch):
+    """bench.py: CUDA events on the launching stream around one C-ABI call + the FLOPs it executes."""
+    if PROFILE is None:
+        launch()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    PROFILE.setdefault(which, []).append((flops, e0, e1, meta))
+
+
 def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bias=None, keymask=None):
     """q/k/v: 2-D views [B*S, >=H*dh] sharing one row stride (e.g. column slices of a packed qkv buffer)."""
     assert q.stride(0) == k.stride(0) == v.stride(0) and q.dtype == k.dtype == v.dtype == o.dtype
-    check(_lib().svla_attn_fwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), o.stride(0), dt(q),
-                               ptr(lse), ptr(traj), ptr(bias), ptr(keymask), B, S, H, dh, scale, stream_ptr()),
-          "svla_attn_fwd")
+    _timed("attn_fwd", 4.0 * B * H * S * S * dh, (mode, B, S, str(q.dtype)[6:]), lambda: check(
+        _lib().svla_attn_fwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), o.stride(0), dt(q),
+                             ptr(lse), ptr(traj), ptr(bias), ptr(keymask), B, S, H, dh, scale, stream_ptr()),
+        "svla_attn_fwd"))
     return o
 
 
 def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, traj=None):
     assert q.stride(0) == k.stride(0) == v.stride(0) and dq.stride(0) == dk.stride(0) == dv.stride(0)
     assert o.stride(0) == d_o.stride(0)
-    check(_lib().svla_attn_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), ptr(d_o), o.stride(0),
-                               ptr(dq), ptr(dk), ptr(dv), dq.stride(0), dt(q), ptr(lse), ptr(traj), B, S, H, dh,
-                               scale, stream_ptr()), "svla_attn_bwd")
+    # five S x S x dh products: the score recompute, dP, dV, dK, dQ
+    _timed("attn_bwd", 10.0 * B * H * S * S * dh, (mode, B, S, str(q.dtype)[6:]), lambda: check(
+        _lib().svla_attn_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), ptr(d_o), o.stride(0),
+                             ptr(dq), ptr(dk), ptr(dv), dq.stride(0), dt(q), ptr(lse), ptr(traj), B, S, H, dh,
+                             scale, stream_ptr()), "svla_attn_bwd"))
 
 
 def attn_cls_fwd(q0, k, v, o, lse, B, S, H=8, dh=64, scale=0.125):

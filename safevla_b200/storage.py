@@ -143,9 +143,8 @@ class B200RolloutStorage:
     def before_updates(self, *, next_value: torch.Tensor, next_c_value: Optional[torch.Tensor] = None,
                        use_gae: bool = True, gamma: float = 0.99, tau: float = 0.95, adv_stats_callback=None,
                        normalize_advantage: bool = False, gae_algo: int = 0, **kwargs):
-        """Bootstrap + GAE(reward) + GAE(cost) + advantages, one launch."""
-        if not use_gae:
-            raise NotImplementedError("use_gae=False is not used by the shipped config")
+        """Bootstrap + GAE(reward) + GAE(cost) + advantages, one launch.  `use_gae=False` (not used
+        by the shipped config) computes the plain discounted returns of the same upstream `compute_returns`."""
         N = self.N
         self.value_preds[self.T].copy_(next_value.to(self.dev).reshape(N, 1))
         K = self.K
@@ -153,11 +152,14 @@ class B200RolloutStorage:
             self.c_value_preds[self.T].copy_(next_c_value.to(self.dev).reshape(N, 1))
         elif next_c_value is not None:  # [N, K] as the cost critic emits it -> channel-major planes
             self.c_value_preds_k[:, self.T].copy_(next_c_value.to(self.dev).reshape(N, K).t().reshape(K, N, 1).clone())
-        ops.gae_dual(self.rewards, self.costs, self.value_preds, self.c_value_preds, self.masks, gamma, tau, gae_algo,
-                     out=(self.returns, self.c_returns, self.adv_targ, self.c_adv_targ))
+        if use_gae:
+            march = lambda r, c, v, cv, out: ops.gae_dual(r, c, v, cv, self.masks, gamma, tau, gae_algo, out=out)  # noqa: E731
+        else:
+            march = lambda r, c, v, cv, out: ops.discounted_returns_dual(r, c, v, cv, self.masks, gamma, out=out)  # noqa: E731
+        march(self.rewards, self.costs, self.value_preds, self.c_value_preds,
+              (self.returns, self.c_returns, self.adv_targ, self.c_adv_targ))
         for k in range(1, K):  # further cost channels: the same march, one stream per launch
-            ops.gae_dual(self.costs_k[k], None, self.c_value_preds_k[k], None, self.masks, gamma, tau, gae_algo,
-                         out=(self.c_returns_k[k], None, self.c_adv_targ_k[k], None))
+            march(self.costs_k[k], None, self.c_value_preds_k[k], None, (self.c_returns_k[k], None, self.c_adv_targ_k[k], None))
         if normalize_advantage:
             self.norm_adv_targ = self._normalized(self.adv_targ, kwargs.get("process_group"))
             self.c_norm_adv_targ_k = torch.stack([self._normalized(self.c_adv_targ_k[k], kwargs.get("process_group"))
@@ -202,7 +204,8 @@ class B200RolloutStorage:
                               "c_adv_targ": ck(self.c_adv_targ_k)})
             if self.norm_adv_targ is not None:
                 batch["norm_adv_targ"] = c(self.norm_adv_targ)
-                batch["c_norm_adv_targ"] = c(self.c_norm_adv_targ)
+                # K > 1: channel-major like c_adv_targ (each channel normalised with its own statistics)
+                batch["c_norm_adv_targ"] = ck(self.c_norm_adv_targ_k) if self.K > 1 else c(self.c_norm_adv_targ)
             yield batch
 
     def after_updates(self, **kwargs):

@@ -66,12 +66,21 @@ class EncStash:
 
 class Tower:
     def __init__(self, weights: TowerWeights, num_actions: int, num_cameras: int, act_dtype: torch.dtype,
-                 cls_only_last_layer: bool = True):
+                 cls_only_last_layer: bool = True, split: int = 0):
         self.W = weights
         self.A, self.C = num_actions, num_cameras
         self.adt = act_dtype  # encoder activation dtype
         self.cls_only = cls_only_last_layer
         self.dev = weights.params.device
+        # parity-grade tensor-core mode: fp32 activations / weights, every tensor-core-shaped product evaluated as
+        # 3 (or 6) split-bf16 products in one tcgen05 launch (ops.gemm split=); 0 = operands as they are
+        self.split = split
+
+    def _gemm(self, a, b, out, **kw):
+        if self.split:
+            kw.setdefault("split", self.split)
+            kw.setdefault("cache_b", not kw.get("trans_a", False))  # B is a weight in forward / dgrad launches
+        return ops.gemm(a, b, out, **kw)
 
     # ------------------------------------------------------------------ helpers
     def _new(self, *shape, dtype=None):
@@ -82,7 +91,7 @@ class Tower:
         b = self.W.p(bname, None, count) if bname else None
         if b is not None:
             b = b.reshape(-1)
-        return ops.gemm(x, w, out, trans_b=True, bias=b, epilogue=epi, residual=residual)
+        return self._gemm(x, w, out, trans_b=True, bias=b, epilogue=epi, residual=residual)
 
     def _lin_bwd(self, dy, x, wname, bname, *, wshape=None, dx=None, aux=None, residual=None, count=1):
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W [* relu'(aux)] [+ residual]."""
@@ -90,12 +99,12 @@ class Tower:
         if gw.dim() != 2:
             gw = gw.view(gw.shape[0], -1)
         gb = self.W.g(bname, None, count).reshape(-1) if bname else None
-        ops.gemm(dy, x, gw, trans_a=True, trans_b=False, accumulate=True, colsum_a=gb)  # dW and db in one launch
+        self._gemm(dy, x, gw, trans_a=True, trans_b=False, accumulate=True, colsum_a=gb)  # dW and db in one launch
         if dx is not None:
             w = self.W.w(wname, wshape, count, dtype=dy.dtype)
             if w.dim() != 2:
                 w = w.view(w.shape[0], -1)
-            ops.gemm(dy, w, dx, trans_b=False, aux=aux, epilogue=EPI_RELU_MASK if aux is not None else EPI_NONE,
+            self._gemm(dy, w, dx, trans_b=False, aux=aux, epilogue=EPI_RELU_MASK if aux is not None else EPI_NONE,
                      residual=residual)
         return dx
 
@@ -161,9 +170,9 @@ class Tower:
                 # everything else for the CLS row only.  Bit-identical to the full layer on row 0.
                 wi = W.w(p + "self_attn.in_proj_weight", dtype=x.dtype)
                 bi = W.p(p + "self_attn.in_proj_bias")
-                kv = ops.gemm(x, wi[D:3 * D], self._new(Ms, 2 * D), trans_b=True, bias=bi[D:3 * D])
+                kv = self._gemm(x, wi[D:3 * D], self._new(Ms, 2 * D), trans_b=True, bias=bi[D:3 * D])
                 xc = x.view(Rc, S * D)[:, :D]  # CLS rows, leading dimension S*D
-                q0 = ops.gemm(xc, wi[0:D], self._new(Rc, D), trans_b=True, bias=bi[0:D])
+                q0 = self._gemm(xc, wi[0:D], self._new(Rc, D), trans_b=True, bias=bi[0:D])
                 ao, lse = self._new(Rc, D), self._new(Rc * H, dtype=torch.float32)
                 ops.attn_cls_fwd(q0, kv[:, 0:D], kv[:, D:2 * D], ao, lse, Rc, S, scale=1.0 / math.sqrt(DH))
                 s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Rc, D),
@@ -228,11 +237,11 @@ class Tower:
                                  t[f"lse_{l}"], Rc, S, scale=1.0 / math.sqrt(DH))
                 xc = x.view(Rc, S * D)[:, :D]
                 # K/V projections of every token
-                ops.gemm(dkv, x, gwi[D:3 * D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[D:3 * D])
-                dxn = ops.gemm(dkv, wi[D:3 * D], self._new(Ms, D), trans_b=False)
+                self._gemm(dkv, x, gwi[D:3 * D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[D:3 * D])
+                dxn = self._gemm(dkv, wi[D:3 * D], self._new(Ms, D), trans_b=False)
                 # Q projection + residual of the CLS row
-                ops.gemm(dq0, xc, gwi[0:D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[0:D])
-                dxc = ops.gemm(dq0, wi[0:D], self._new(Rc, D), trans_b=False, residual=ds1)
+                self._gemm(dq0, xc, gwi[0:D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[0:D])
+                dxc = self._gemm(dq0, wi[0:D], self._new(Rc, D), trans_b=False, residual=ds1)
                 ops.copy_rows(dxc, dxn, Rc, D, dmap=RowMap(1, S, 0), accumulate=True)
                 dx = dxn
             else:
@@ -290,32 +299,32 @@ class Tower:
             p = f"decoder.layers.{l}."
             r1 = self._new(Md, dtype=f32)
             y1 = ops.rmsnorm_fwd(h, W.p(p + "attention_norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, r1)
-            qkv = ops.gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, 3 * D, dtype=ddt))
+            qkv = self._gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, 3 * D, dtype=ddt))
             ao, lse = self._new(Md, D, dtype=ddt), self._new(N * H * T, dtype=f32)
             ops.attn_fwd(ATTN_TRAJ_CAUSAL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, lse, N, T,
                          scale=1.0 / math.sqrt(DH), traj=traj_nt)
-            h2 = ops.gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h)
+            h2 = self._gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h)
             r2 = self._new(Md, dtype=f32)
             y2 = ops.rmsnorm_fwd(h2, W.p(p + "ffn_norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, r2)
-            ab = ops.gemm(y2, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
+            ab = self._gemm(y2, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
                           self._new(Md, 2 * DEC_FF, dtype=ddt))
             g = ops.swiglu_fwd(ab, self._new(Md, DEC_FF, dtype=ddt))
-            h3 = ops.gemm(g, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h2)
+            h3 = self._gemm(g, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h2)
             if keep:
                 t.update({f"h_{l}": h, f"r1_{l}": r1, f"y1_{l}": y1, f"qkv_{l}": qkv, f"ao_{l}": ao, f"lse_{l}": lse,
                           f"h2_{l}": h2, f"r2_{l}": r2, f"y2_{l}": y2, f"ab_{l}": ab, f"g_{l}": g})
             h = h3
         rf = self._new(Md, dtype=f32)
         yf = ops.rmsnorm_fwd(h, W.p("decoder.norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, rf)
-        b_nt = ops.gemm(yf, W.w("decoder.output.weight", dtype=ddt), self._new(Md, D, dtype=f32))
+        b_nt = self._gemm(yf, W.w("decoder.output.weight", dtype=ddt), self._new(Md, D, dtype=f32))
         b_tn = ops.copy_rows(b_nt, self._new(Md, D, dtype=f32), Md, D, idx=perm_tn)
         out = {}
         if want_logits:
-            out["logits"] = ops.gemm(b_tn, W.p("actor.linear.weight"), self._new(Md, self.A, dtype=f32),
+            out["logits"] = self._gemm(b_tn, W.p("actor.linear.weight"), self._new(Md, self.A, dtype=f32),
                                      bias=W.p("actor.linear.bias")).view(T, N, self.A)
         if want_values:
             nv = W.p("critic.fc.weight").shape[0]  # 1, or K for the cost tower of the K-cost-channel extension
-            out["values"] = ops.gemm(b_tn, W.p("critic.fc.weight"), self._new(Md, nv, dtype=f32),
+            out["values"] = self._gemm(b_tn, W.p("critic.fc.weight"), self._new(Md, nv, dtype=f32),
                                      bias=W.p("critic.fc.bias")).view(T, N, nv)
         if keep:
             t.update({"hf": h, "rf": rf, "yf": yf, "b_tn": b_tn})
@@ -338,26 +347,26 @@ class Tower:
             p = f"decoder.layers.{l}."
             ck, cv = cache[l]
             y1 = ops.rmsnorm_fwd(h, W.p(p + "attention_norm.weight"), self._new(N, D, dtype=ddt), RMS_EPS)
-            qkv = ops.gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(N, 3 * D, dtype=ddt))
+            qkv = self._gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(N, 3 * D, dtype=ddt))
             ops.copy_rows(qkv[:, D:2 * D], ck.view(-1, D), N, D, dmap=RowMap(1, ck.shape[1], pos))
             ops.copy_rows(qkv[:, 2 * D:3 * D], cv.view(-1, D), N, D, dmap=RowMap(1, cv.shape[1], pos))
             ao = ops.attn_decode(qkv[:, 0:D], ck, cv, time_step, pos, self._new(N, D, dtype=ddt),
                                  scale=1.0 / math.sqrt(DH))
-            h2 = ops.gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(N, D, dtype=f32), residual=h)
+            h2 = self._gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(N, D, dtype=f32), residual=h)
             y2 = ops.rmsnorm_fwd(h2, W.p(p + "ffn_norm.weight"), self._new(N, D, dtype=ddt), RMS_EPS)
-            ab = ops.gemm(y2, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
+            ab = self._gemm(y2, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
                           self._new(N, 2 * DEC_FF, dtype=ddt))
             g = ops.swiglu_fwd(ab, self._new(N, DEC_FF, dtype=ddt))
-            h = ops.gemm(g, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(N, D, dtype=f32), residual=h2)
+            h = self._gemm(g, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(N, D, dtype=f32), residual=h2)
         yf = ops.rmsnorm_fwd(h, W.p("decoder.norm.weight"), self._new(N, D, dtype=ddt), RMS_EPS)
-        b = ops.gemm(yf, W.w("decoder.output.weight", dtype=ddt), self._new(N, D, dtype=f32))
+        b = self._gemm(yf, W.w("decoder.output.weight", dtype=ddt), self._new(N, D, dtype=f32))
         out = {}
         if want_logits:
-            out["logits"] = ops.gemm(b, W.p("actor.linear.weight"), self._new(N, self.A, dtype=f32),
+            out["logits"] = self._gemm(b, W.p("actor.linear.weight"), self._new(N, self.A, dtype=f32),
                                      bias=W.p("actor.linear.bias")).view(1, N, self.A)
         if want_values:
             nv = W.p("critic.fc.weight").shape[0]
-            out["values"] = ops.gemm(b, W.p("critic.fc.weight"), self._new(N, nv, dtype=f32),
+            out["values"] = self._gemm(b, W.p("critic.fc.weight"), self._new(N, nv, dtype=f32),
                                      bias=W.p("critic.fc.bias")).view(1, N, nv)
         return out
 
@@ -372,45 +381,45 @@ class Tower:
         db_tn = None
         if dlogits is not None:
             dl = dlogits.view(Md, self.A)
-            ops.gemm(dl, t["b_tn"], W.g("actor.linear.weight"), trans_a=True, trans_b=False, accumulate=True)
+            self._gemm(dl, t["b_tn"], W.g("actor.linear.weight"), trans_a=True, trans_b=False, accumulate=True)
             ops.colsum(dl, W.g("actor.linear.bias"), accumulate=True)
-            db_tn = ops.gemm(dl, W.p("actor.linear.weight"), self._new(Md, D, dtype=f32), trans_b=False)
+            db_tn = self._gemm(dl, W.p("actor.linear.weight"), self._new(Md, D, dtype=f32), trans_b=False)
         if dvalues is not None:
             dv = dvalues.view(Md, -1)
-            ops.gemm(dv, t["b_tn"], W.g("critic.fc.weight"), trans_a=True, trans_b=False, accumulate=True)
+            self._gemm(dv, t["b_tn"], W.g("critic.fc.weight"), trans_a=True, trans_b=False, accumulate=True)
             ops.colsum(dv, W.g("critic.fc.bias"), accumulate=True)
-            db_tn = ops.gemm(dv, W.p("critic.fc.weight"), self._new(Md, D, dtype=f32), trans_b=False,
+            db_tn = self._gemm(dv, W.p("critic.fc.weight"), self._new(Md, D, dtype=f32), trans_b=False,
                              residual=db_tn)
         db_nt = ops.copy_rows(db_tn, self._new(Md, D, dtype=ddt), Md, D, idx=perm_nt)
-        ops.gemm(db_nt, t["yf"], W.g("decoder.output.weight"), trans_a=True, trans_b=False, accumulate=True)
-        dyf = ops.gemm(db_nt, W.w("decoder.output.weight", dtype=ddt), self._new(Md, D, dtype=ddt), trans_b=False)
+        self._gemm(db_nt, t["yf"], W.g("decoder.output.weight"), trans_a=True, trans_b=False, accumulate=True)
+        dyf = self._gemm(db_nt, W.w("decoder.output.weight", dtype=ddt), self._new(Md, D, dtype=ddt), trans_b=False)
         dh = ops.rmsnorm_bwd(dyf, t["hf"], W.p("decoder.norm.weight"), t["rf"], self._new(Md, D, dtype=f32),
                              W.g("decoder.norm.weight"))
         for l in (2, 1, 0):
             p = f"decoder.layers.{l}."
             dh_o = operand(dh)
-            ops.gemm(dh_o, t[f"g_{l}"], W.g(p + "feed_forward.w2.weight"), trans_a=True, trans_b=False, accumulate=True)
-            dg = ops.gemm(dh_o, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(Md, DEC_FF, dtype=ddt),
+            self._gemm(dh_o, t[f"g_{l}"], W.g(p + "feed_forward.w2.weight"), trans_a=True, trans_b=False, accumulate=True)
+            dg = self._gemm(dh_o, W.w(p + "feed_forward.w2.weight", dtype=ddt), self._new(Md, DEC_FF, dtype=ddt),
                           trans_b=False)
             dab = ops.swiglu_bwd(t[f"ab_{l}"], dg, self._new(Md, 2 * DEC_FF, dtype=ddt))
-            ops.gemm(dab, t[f"y2_{l}"], W.g(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2), trans_a=True,
+            self._gemm(dab, t[f"y2_{l}"], W.g(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2), trans_a=True,
                      trans_b=False, accumulate=True)
-            dy2 = ops.gemm(dab, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
+            dy2 = self._gemm(dab, W.w(p + "feed_forward.w1.weight", (2 * DEC_FF, D), 2, dtype=ddt),
                            self._new(Md, D, dtype=ddt), trans_b=False)
             ops.rmsnorm_bwd(dy2, t[f"h2_{l}"], W.p(p + "ffn_norm.weight"), t[f"r2_{l}"], dh,
                             W.g(p + "ffn_norm.weight"), accumulate_dx=True)  # dh := d h2
             ao = t[f"ao_{l}"]
             dh_o = operand(dh)
-            ops.gemm(dh_o, ao, W.g(p + "attention.wo.weight"), trans_a=True, trans_b=False, accumulate=True)
-            dao = ops.gemm(dh_o, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=ddt), trans_b=False)
+            self._gemm(dh_o, ao, W.g(p + "attention.wo.weight"), trans_a=True, trans_b=False, accumulate=True)
+            dao = self._gemm(dh_o, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=ddt), trans_b=False)
             qkv = t[f"qkv_{l}"]
             dqkv = self._new(Md, 3 * D, dtype=ddt)
             ops.attn_bwd(ATTN_TRAJ_CAUSAL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, dao, dqkv[:, 0:D],
                          dqkv[:, D:2 * D], dqkv[:, 2 * D:3 * D], t[f"lse_{l}"], N, T, scale=1.0 / math.sqrt(DH),
                          traj=traj_nt)
-            ops.gemm(dqkv, t[f"y1_{l}"], W.g(p + "attention.wq.weight", (3 * D, D), 3), trans_a=True, trans_b=False,
+            self._gemm(dqkv, t[f"y1_{l}"], W.g(p + "attention.wq.weight", (3 * D, D), 3), trans_a=True, trans_b=False,
                      accumulate=True)
-            dy1 = ops.gemm(dqkv, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, D, dtype=ddt),
+            dy1 = self._gemm(dqkv, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, D, dtype=ddt),
                            trans_b=False)
             ops.rmsnorm_bwd(dy1, t[f"h_{l}"], W.p(p + "attention_norm.weight"), t[f"r1_{l}"], dh,
                             W.g(p + "attention_norm.weight"), accumulate_dx=True)  # dh := d h
@@ -426,13 +435,16 @@ class T5Encoder:
     bf16 mode: bf16 GEMM operands from a bf16 copy of the frozen weights on the tcgen05 kernels, fp32 residual
     stream and fp32 accumulation -- the same split as the decoder."""
 
-    def __init__(self, layout: T5Layout, arena: torch.Tensor, act_dtype: torch.dtype = torch.float32):
+    def __init__(self, layout: T5Layout, arena: torch.Tensor, act_dtype: torch.dtype = torch.float32, split: int = 0):
         self.layout, self.arena = layout, arena
         self.dev = arena.device
         self.adt = act_dtype
+        self.split = split
         self.shadow: Optional[torch.Tensor] = None
         self._bias_cache: Dict[int, torch.Tensor] = {}
         self.refresh()
+
+    _gemm = Tower._gemm
 
     def refresh(self):
         """Re-derive everything computed from the frozen weights (call after they are loaded)."""
@@ -469,13 +481,13 @@ class T5Encoder:
         for i in range(6):
             a = f"encoder.block.{i}.layer.0."
             y = ops.rmsnorm_fwd(x, self.w(a + "layer_norm.weight"), new(M, D, dtype=odt), T5_EPS)
-            qkv = ops.gemm(y, self.w(a + "SelfAttention.q.weight", (3 * D, D), 3, operand=True), new(M, 3 * D, dtype=odt))
+            qkv = self._gemm(y, self.w(a + "SelfAttention.q.weight", (3 * D, D), 3, operand=True), new(M, 3 * D, dtype=odt))
             ao = ops.attn_fwd(ATTN_T5_BIAS, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], new(M, D, dtype=odt), None,
                               U, L, scale=1.0, bias=bias, keymask=km)
-            x = ops.gemm(ao, self.w(a + "SelfAttention.o.weight", operand=True), new(M, D), residual=x)
+            x = self._gemm(ao, self.w(a + "SelfAttention.o.weight", operand=True), new(M, D), residual=x)
             f = f"encoder.block.{i}.layer.1."
             y = ops.rmsnorm_fwd(x, self.w(f + "layer_norm.weight"), new(M, D, dtype=odt), T5_EPS)
-            hf = ops.gemm(y, self.w(f + "DenseReluDense.wi.weight", operand=True), new(M, FF, dtype=odt),
+            hf = self._gemm(y, self.w(f + "DenseReluDense.wi.weight", operand=True), new(M, FF, dtype=odt),
                           epilogue=EPI_RELU)
-            x = ops.gemm(hf, self.w(f + "DenseReluDense.wo.weight", operand=True), new(M, D), residual=x)
+            x = self._gemm(hf, self.w(f + "DenseReluDense.wo.weight", operand=True), new(M, D), residual=x)
         return ops.rmsnorm_fwd(x, self.w("encoder.final_layer_norm.weight"), new(M, D), T5_EPS)

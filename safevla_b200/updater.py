@@ -154,6 +154,37 @@ class PPOLagUpdater:
         self.lagrange.update_from_sum_count(cost_pair)
         return {"loss_scalars": scal, "lambda": self.lagrange.lagrangian_multiplier, "grad_sq_norm": self.sq}
 
+    # ------------------------------------------------------------------ resume state
+    def state_dict(self) -> Dict:
+        """Everything a resumed run needs besides the model's own state_dict (checkpoint row: the
+        reference engine saves `optimizer_state_dict` next to `model_state_dict`, training/online/
+        dinov2_vits_tsfm_base.py:79,329): Adam moments as flat fp32 arenas in ParamLayout order, the per-tower step
+        counts (torch.optim.Adam keeps one per parameter; towers start counting when they first train) and the
+        Lagrange multiplier with its own Adam state."""
+        return {"exp_avg": self.exp_avg.detach().cpu().clone(), "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(),
+                "adam_step": self.adam_step, "tower_steps": list(self.tower_steps),
+                "layout_total": self.model.layout.total,
+                "lagrange": {k: v.detach().cpu() for k, v in self.lagrange.state_dict().items()}}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        if sd["layout_total"] != self.model.layout.total:
+            raise ValueError("optimizer state belongs to a model with a different parameter layout")
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.adam_step, self.tower_steps = int(sd["adam_step"]), [int(x) for x in sd["tower_steps"]]
+        self.lagrange.load_state_dict({k: v.to(self.model.dev) for k, v in sd["lagrange"].items()})
+
+    def named_optimizer_state(self) -> Dict[str, Dict]:
+        """torch.optim.Adam-style view of the flat state: {parameter name: {exp_avg, exp_avg_sq, step}} (views, no
+        copies) -- what a tool that inspects or converts a reference checkpoint's optimizer state expects."""
+        from .params import TOWERS
+        lay, out = self.model.layout, {}
+        for name in lay.slots:
+            ti = max(i for i, pre in enumerate(TOWERS) if name.startswith(pre))
+            out[name] = {"exp_avg": lay.view(self.exp_avg, name), "exp_avg_sq": lay.view(self.exp_avg_sq, name),
+                         "step": self.tower_steps[ti]}
+        return out
+
     def _reduce_clip_step(self, storage: B200RolloutStorage, last: bool):
         m, c = self.model, self.cfg
         n = m.layout.total
@@ -180,3 +211,4 @@ class PPOLagUpdater:
             ops.clip_adam(m.param_arena[a:b], m.grad_arena[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
                           m.shadow_arena[a:b] if m.shadow_arena is not None else None,
                           self.sq if c.max_grad_norm > 0 else None, hp)
+        ops.split_cache_clear()  # split-operand copies of the weights (bf16x3 / bf16x6 modes) are stale now

@@ -1,0 +1,191 @@
+"""Parity of the paths bench.py TIMES (bf16 tcgen05 and the split-operand parity-grade tensor-core mode) against the
+reference goldens and the CPU oracle -- not only of the fp32 FMA mode:
+
+  * the T128_N1_A20_C1 golden (a full 128-step decoder window, 20 actions, minted from the unmodified reference) on
+    the GPU in every precision: logits / log-probs / values, the four SafePPOLogGrad scalars, every parameter-gradient
+    norm and ten gradients in full;
+  * a whole PPO-Lagrangian update (two repeats) in the fast modes against oracle/update_oracle.py;
+  * sampler columns of the ACTUAL cfg 2 bench rollout (64 env x 128 step, seed 1234, random-init weights seed 0)
+    against the CPU oracle run on those samplers alone.
+
+Tolerances are the measured errors (gpurun_out/fastpath_parity.json is rewritten by every run) with head-room, and
+are stated per precision in TOL below.  B200 only."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_oracle as TO  # noqa: E402  (checker only)
+from oracle.make_golden import GOLDEN_DIR, build_inputs  # noqa: E402
+from safevla_b200.params import init_state_dict  # noqa: E402
+from safevla_b200.synthetic import RolloutSpec, make_rollout, prev_actions_from  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = os.path.join(ROOT, "gpurun_out", "fastpath_parity.json")
+
+# relative tolerances (max |err| / max |ref|) per precision:
+#   fwd   logits / log-probs / values / cost values          loss  the four loss scalars
+#   gnorm every parameter-gradient L2 norm                    grad  the ten full gradient tensors
+# fp32 and bf16x3 meet BASELINE's 1e-4 gate; bf16 rounds every GEMM operand to 8 mantissa bits (2^-9 relative).
+TOL = {
+    "fp32": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3),
+    "bf16x3": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3),
+    "bf16x6": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3),
+    "bf16": dict(fwd=3e-2, loss=2e-2, gnorm=5e-2, grad=8e-2),
+}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    return ((a.double().cpu() - b.double().cpu()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+
+
+def _report(key, rec):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    data = {}
+    if os.path.exists(REPORT):
+        try:
+            data = json.load(open(REPORT))
+        except Exception:
+            data = {}
+    data[key] = rec
+    json.dump(data, open(REPORT, "w"), indent=1, sort_keys=True)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["T128_N1_A20_C1", "cfg1_T16_N1_A6_C1", "T12_N2_A20_C2"])
+def test_reference_golden_every_precision(dev, name, precision):
+    from safevla_b200.losses import SafePPOLogGrad
+    from safevla_b200.model import B200SafeActorCritic
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    case = gold["case"]
+    sd = init_state_dict(case["A"], case["C"], case["wseed"], actor_gain=1.0)
+    model = B200SafeActorCritic(case["A"], case["C"], precision=precision, state_dict=sd, device=dev)
+    _, ro, extra = build_inputs(case)
+    obs = {k: v[:-1].to(dev) for k, v in ro["observations"].items()}
+    out, _ = model(obs, None, prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev))
+    tol, rec = TOL[precision], {}
+    rec["logits"] = relerr(out.distributions.raw_logits, gold["logits"])
+    rec["log_probs"] = relerr(out.distributions.logits, gold["log_probs"])
+    rec["values"] = relerr(out.values, gold["values"])
+    rec["c_values"] = relerr(out.c_values, gold["c_values"])
+    ret, adv = TO.gae_returns(ro["rewards"], extra["value_preds"], ro["masks"], 0.99, 0.95)
+    _, cadv = TO.gae_returns(ro["costs"], extra["c_value_preds"], ro["masks"], 0.99, 0.95)
+    batch = {"actions": ro["actions"].to(dev), "old_action_log_probs": gold["old_logp"].to(dev),
+             "adv_targ": adv.to(dev), "c_adv_targ": cadv.to(dev), "values": extra["value_preds"][:-1].to(dev),
+             "returns": ret[:-1].to(dev)}
+    loss = SafePPOLogGrad(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.01, use_clipped_value_loss=False,
+                          action_loss_schedule=None, discrete_critics=False, normalize_advantage=False)
+    total, info = loss.loss(0, batch, out, lagrangian_multiplier=torch.tensor(case["lam"]))
+    for k in ("ppo_total", "value", "action", "entropy"):
+        rec["loss_" + k] = abs(info[k] - gold["info"][k]) / max(1.0, abs(gold["info"][k]))
+    total.backward()
+    worst = ("", 0.0)
+    for k, gn in gold["grad_norms"].items():
+        p = model.get_parameter(k)
+        if gn is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+            continue
+        err = abs(p.grad.norm().item() - gn) / max(gn, 1e-8)
+        if err > worst[1]:
+            worst = (k, err)
+    rec["grad_norm_worst"], rec["grad_norm_worst_key"] = worst[1], worst[0]
+    gworst = ("", 0.0)
+    for k, gref in gold["grads"].items():
+        err = relerr(model.get_parameter(k).grad, gref)
+        if err > gworst[1]:
+            gworst = (k, err)
+    rec["grad_full_worst"], rec["grad_full_worst_key"] = gworst[1], gworst[0]
+    _report(f"golden/{name}/{precision}", rec)
+    for k in ("logits", "log_probs", "values", "c_values"):
+        assert rec[k] < tol["fwd"], (k, rec)
+    for k in ("ppo_total", "value", "action", "entropy"):
+        assert rec["loss_" + k] < tol["loss"], (k, rec)
+    assert rec["grad_norm_worst"] < tol["gnorm"], rec
+    assert rec["grad_full_worst"] < tol["grad"], rec
+
+
+@pytest.mark.parametrize("precision,tol_delta,tol_lam", [("bf16x3", 2e-3, 1e-5), ("bf16", 0.25, 1e-5)])
+def test_whole_update_fast_modes_vs_oracle(dev, precision, tol_delta, tol_lam):
+    """PPOLagUpdater.update (GAE -> 2 x [3-tower fwd, fused loss, bwd, clip, Adam] -> lambda) in the tensor-core modes
+    against the CPU oracle.  The comparison is on the parameter MOVEMENT (Adam's first steps are sign-like, so the
+    movement is O(lr) per element and an operand-rounding error shows up as a fraction of it):
+        max |delta_mine - delta_ref| / max |delta_ref| ,   the loss of the last repeat,   lambda."""
+    from oracle.update_oracle import oracle_update
+    from safevla_b200.model import B200SafeActorCritic
+    from safevla_b200.storage import B200RolloutStorage
+    from safevla_b200.updater import PPOLagConfig, PPOLagUpdater
+    T, N, A, C = 8, 2, 6, 1
+    sd = init_state_dict(A, C, seed=21, actor_gain=1.0)
+    ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.2, seed=77))
+    g = torch.Generator().manual_seed(5)
+    vp, cvp = torch.randn(T + 1, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g).abs()
+    logp = -1.7 + 0.1 * torch.randn(T, N, generator=g)
+    cfg = PPOLagConfig(update_repeats=2, lr=1e-3, eps=1e-4)  # eps: see test_updater_matches_oracle_update
+    ref_sd, ref_lam, ref_info = oracle_update(sd, ro, vp, cvp, logp, cfg, A, C)
+    model = B200SafeActorCritic(A, C, precision=precision, state_dict=sd, device=dev)
+    st = B200RolloutStorage(T, dev)
+    st.load_rollout(ro, vp, cvp, logp)
+    res = PPOLagUpdater(model, cfg).update(st)
+    mine = model.state_dict()
+    num = den = 0.0
+    l2n = l2d = 0.0
+    for k, v in ref_sd.items():
+        if "text_encoder" in k:
+            continue
+        d_ref, d_mine = (v - sd[k]).double(), (mine[k].cpu() - sd[k]).double()
+        num, den = max(num, (d_mine - d_ref).abs().max().item()), max(den, d_ref.abs().max().item())
+        l2n, l2d = l2n + (d_mine - d_ref).pow(2).sum().item(), l2d + d_ref.pow(2).sum().item()
+    rec = {"delta_max_rel": num / den, "delta_l2_rel": (l2n / l2d) ** 0.5,
+           "loss_rel": abs(res["loss_scalars"][0].item() - ref_info["last_total"]) / max(1.0, abs(ref_info["last_total"])),
+           "lambda_abs": abs(res["lambda"].item() - ref_lam)}
+    _report(f"update/{precision}", rec)
+    assert den > 5e-4
+    assert rec["lambda_abs"] < tol_lam, rec
+    assert rec["loss_rel"] < (1e-4 if precision != "bf16" else 2e-2), rec
+    assert rec["delta_l2_rel"] < tol_delta, rec
+
+
+def test_cfg2_bench_rollout_sampler_columns_vs_oracle(dev):
+    """The rollout and the weights bench.py's default run uses (cfg2: T = 128, N = 64, A = 20, seeds 1234 / 0), bf16,
+    the bench's chunking: the three towers' outputs for sampler columns 0 and 63 against the CPU oracle evaluated on
+    those samplers alone (rows of different samplers never interact), and the fused loss + its logit gradient on
+    those columns against the oracle's autograd."""
+    from safevla_b200.model import ACTOR, COST, CRITIC, B200SafeActorCritic
+    T, N, A, C = 128, 64, 20, 1
+    ro = make_rollout(RolloutSpec(T, N, A, C, prompt_tokens=32, seed=1234))
+    sd = init_state_dict(A, C, seed=0)
+    model = B200SafeActorCritic(A, C, precision="bf16", state_dict=sd, device=dev, chunk_rows=4096, extras="off")
+    obs = {k: v[:T].to(dev) for k, v in ro["observations"].items()}
+    prev = prev_actions_from(ro["actions"])
+    with torch.no_grad():
+        rc = model.prepare(obs, T, N)
+        mk = ro["masks"][:T].to(dev).view(T, N).contiguous()
+        outs = {i: model.tower_forward(i, rc, prev.to(dev).contiguous(), mk, keep=False, want_logits=(i == ACTOR),
+                                       want_values=(i != ACTOR))[0] for i in (ACTOR, CRITIC, COST)}
+    torch.set_num_threads(os.cpu_count() or 1)
+    rec = {}
+    for col in (0, 63):
+        sl = slice(col, col + 1)
+        obs_c = {k: v[:T, sl] for k, v in ro["observations"].items()}
+        with torch.no_grad():
+            ref = TO.safe_model_forward(sd, obs_c, prev[:, sl], ro["masks"][:T, sl], A, C)
+        rec[f"logits_col{col}"] = relerr(outs[ACTOR]["logits"][:, sl], ref["logits"])
+        rec[f"values_col{col}"] = relerr(outs[CRITIC]["values"][:, sl], ref["values"])
+        rec[f"c_values_col{col}"] = relerr(outs[COST]["values"][:, sl], ref["c_values"])
+        # the action distribution the update differentiates: total-variation distance per row, worst row
+        p_mine = torch.softmax(outs[ACTOR]["logits"][:, sl].float().cpu(), -1)
+        p_ref = torch.softmax(ref["logits"], -1)
+        rec[f"tv_col{col}"] = 0.5 * (p_mine - p_ref).abs().sum(-1).max().item()
+    _report("cfg2_bench_rollout/bf16", rec)
+    for k, v in rec.items():
+        assert v < (3e-2 if not k.startswith("tv") else 1e-2), (k, rec)

@@ -193,9 +193,14 @@ def test_lagrange_update(dev):
     for jc in [4.0, 1.0, 0.2, 0.0, 0.0, 0.0, 3.0, 0.1, 0.0, 0.0]:
         lag.update_lagrange_multiplier(jc)
         assert abs(lag.lagrangian_multiplier.item() - orc.update(jc)) < 1e-5
+    # zero-episode rollout KAT: no finished episode -> no Jc estimate -> lambda AND its Adam state stay untouched
     lag2 = Lagrange(1.0, lagrangian_multiplier_init=0.01, device=dev)
-    lag2.update_from_sum_count(torch.tensor([0.0, 0.0], device=dev))  # no finished episode: Jc = 0 -> lambda -> 0
-    assert lag2.lagrangian_multiplier.item() == 0.0
+    lag2.update_from_sum_count(torch.tensor([7.0, 3.0], device=dev))
+    lam_before, st_before = lag2.lagrangian_multiplier.clone(), lag2.state.clone()
+    lag2.update_from_sum_count(torch.tensor([0.0, 0.0], device=dev))
+    assert torch.equal(lag2.lagrangian_multiplier, lam_before) and torch.equal(lag2.state, st_before)
+    lag2.update_from_sum_count(torch.tensor([0.0, 2.0], device=dev))  # finished episodes with zero cost DO count
+    assert lag2.lagrangian_multiplier.item() < lam_before.item() and lag2.state[0, 2].item() == 2.0
 
 
 @pytest.mark.parametrize("n", [64, 4096 * 33, 21_000_000])
@@ -675,3 +680,99 @@ def test_gemm_tcgen05_strided_and_repeat(dev):
     _ops().gemm(x[:, :D], w, qkv, trans_b=True, impl=2)
     ref = x[:, :D].double() @ w.double().t()
     assert (qkv.double() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------ use_gae = False
+@pytest.mark.parametrize("T,N", [(16, 1), (128, 64), (5, 3), (1, 7), (257, 33), (40, 5000)])
+def test_discounted_returns_dual_bit_exact(dev, T, N):
+    """The `use_gae=False` branch of compute_returns: bit-exact against the sequential loop on both
+    streams, and against the plain-C restatement oracle/c/gae_ref.c::discounted_returns_f32."""
+    import ctypes as C
+    import numpy as np
+    from oracle.c import build as oracle_c
+    g = torch.Generator().manual_seed(T * 131 + N)
+    r = torch.randn(T, N, 1, generator=g)
+    c = (torch.rand(T, N, 1, generator=g) < 0.2).float()
+    v = torch.randn(T + 1, N, 1, generator=g)
+    vc = torch.randn(T + 1, N, 1, generator=g)
+    m = (torch.rand(T + 1, N, 1, generator=g) > 0.1).float()
+    ret, adv = TO.gae_returns(r, v, m, 0.99, 0.95, use_gae=False)
+    cret, cadv = TO.gae_returns(c, vc, m, 0.99, 0.95, use_gae=False)
+    got = [t.cpu() for t in _ops().discounted_returns_dual(r.to(dev), c.to(dev), v.to(dev), vc.to(dev), m.to(dev), 0.99)]
+    assert torch.equal(got[0], ret) and torch.equal(got[1], cret)
+    assert torch.equal(got[2], adv) and torch.equal(got[3], cadv)
+    one = [t.cpu() for t in _ops().discounted_returns_dual(r.to(dev), None, v.to(dev), None, m.to(dev), 0.99)]
+    assert torch.equal(one[0], ret) and one[1] is None and torch.equal(one[2], adv)
+    lib = C.CDLL(oracle_c.build())
+    out = np.zeros((T + 1, N), dtype=np.float32)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rn, vn, mn = (np.ascontiguousarray(t.reshape(t.shape[0], N).numpy()) for t in (r, v, m))
+    lib.discounted_returns_f32(fp(rn), fp(vn), fp(mn), fp(out), C.c_int(T), C.c_int(N), C.c_double(0.99))
+    assert np.array_equal(out, ret.reshape(T + 1, N).numpy())
+
+
+def test_storage_use_gae_false(dev):
+    from safevla_b200.storage import B200RolloutStorage
+    from safevla_b200.synthetic import RolloutSpec, make_rollout
+    T, N = 12, 4
+    ro = make_rollout(RolloutSpec(T, N, 6, 1, episode_end_prob=0.2, seed=3))
+    g = torch.Generator().manual_seed(0)
+    vp, cvp = torch.randn(T + 1, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g).abs()
+    st = B200RolloutStorage(T, dev)
+    st.load_rollout(ro, vp, cvp, torch.zeros(T, N))
+    st.before_updates(next_value=vp[T], next_c_value=cvp[T], use_gae=False, gamma=0.97)
+    ret, adv = TO.gae_returns(ro["rewards"], vp, ro["masks"], 0.97, 0.95, use_gae=False)
+    cret, cadv = TO.gae_returns(ro["costs"], cvp, ro["masks"], 0.97, 0.95, use_gae=False)
+    assert torch.equal(st.returns.cpu(), ret) and torch.equal(st.adv_targ.cpu(), adv)
+    assert torch.equal(st.c_returns.cpu(), cret) and torch.equal(st.c_adv_targ.cpu(), cadv)
+
+
+# ------------------------------------------------------------------------------------------ split-operand GEMM
+@pytest.mark.parametrize("rows,cols,ld", [(64, 64, 64), (1000, 512, 512), (300, 128, 640), (5, 2048, 2048)])
+def test_split_concat_parts(dev, rows, cols, ld):
+    """p0 + p1 (+ p2) reproduces x to 2^-16 (2^-24) relative; layouts of both concatenation axes."""
+    g = torch.Generator().manual_seed(rows + cols)
+    base = (torch.randn(rows, ld, generator=g) * torch.exp(3 * torch.randn(rows, ld, generator=g))).to(dev)
+    x = base[:, :cols]
+    for axis in (1, 0):
+        out = _ops().split_concat(x, ld, rows, cols, axis, (0, 1, 2, 1))
+        parts = [out[:, j * cols:(j + 1) * cols] if axis == 1 else out[j * rows:(j + 1) * rows] for j in range(4)]
+        p0, p1, p2 = parts[0].float(), parts[1].float(), parts[2].float()
+        assert torch.equal(parts[3], parts[1])
+        assert torch.equal(p0, x.bfloat16().float())
+        assert torch.equal(p1, (x - p0).bfloat16().float())
+        assert torch.equal(p2, (x - p0 - p1).bfloat16().float())
+        assert ((p0 + p1 - x).abs() <= 2.0 ** -16 * x.abs()).all()
+        assert ((p0 + p1 + p2 - x).abs() <= 2.0 ** -23 * x.abs() + 1e-38).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1872, 1536, 512), (1000, 384, 2048), (117 * 64, 512, 512),
+                                   (300, 64, 100)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False)])
+@pytest.mark.parametrize("split,tol", [(3, 3e-5), (6, 2e-6)])
+def test_gemm_split_operand_matches_fp64(dev, M, N, K, ta, tb, split, tol):
+    """fp32 operands through the bf16 tcgen05 kernels as 3 (6) split products in ONE launch, against fp64:
+    error relative to sum_k |a||b| (the fp32-FMA kernel itself sits at ~1e-6 on this measure)."""
+    L = _L()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g).to(dev)
+    b = torch.randn((N, K) if tb else (K, N), generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    out = torch.empty(M, N, device=dev)
+    l0 = L.load_library().svla_launch_count()
+    _ops().gemm(a, b, out, trans_a=ta, trans_b=tb, bias=bias, residual=res, epilogue=L.EPI_NONE, split=split)
+    A64, B64 = (a.t() if ta else a).double(), (b.t() if tb else b).double()
+    ref = A64 @ B64 + bias.double() + res.double()
+    scale = (A64.abs() @ B64.abs()).max().item()
+    err = (out.double() - ref).abs().max().item() / scale
+    assert err < tol, err
+    if K % 4 == 0 and M >= 64:  # two staging launches + ONE GEMM launch (tensor-core shapes)
+        assert L.load_library().svla_launch_count() - l0 == 3
+    # weight-gradient form: accumulate + fused bias gradient stays exact
+    if ta and not tb:
+        acc = torch.randn(M, N, generator=g).to(dev)
+        out2, cs = acc.clone(), torch.zeros(M, device=dev)
+        _ops().gemm(a, b, out2, trans_a=True, trans_b=False, accumulate=True, colsum_a=cs, split=split)
+        assert ((out2.double() - (acc.double() + A64 @ B64)).abs().max().item() / scale) < tol
+        assert torch.allclose(cs, a.sum(0), rtol=1e-4, atol=1e-3)
