@@ -277,7 +277,17 @@ extern "C" int svla_attn_decode(svla_ctx* ctx, const void* q, long long ldq, con
                                 long long ldo, int dtype, int N, int H, int dh, float scale, int q_per_cache,
                                 svla_stream stream);
 static inline bool lse_needed_beyond_flash(const float* lse, int dtype) { return lse != nullptr && dtype != SVLA_BF16; }
-static int g_attn_impl = 0;  // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel (error when unsupported)
+// attn_ws.cu: warp-specialised persistent tcgen05 kernels (S <= 128), the default for bf16
+bool svla_attn_ws_supported(int mode, int dtype, int S, int dh, long long ld, long long ldo, const void* q, const void* k,
+                            const void* v, const void* o);
+int svla_attn_ws_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                     long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st);
+int svla_attn_ws_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* d_o,
+                     long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse, const int64_t* traj,
+                     int B, int S, int H, float scale, cudaStream_t st);
+// 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel (error when unsupported), 3 the round-1 one-CTA-per-item tcgen05 kernels
+// of attn_tc.cu instead of the warp-specialised ones (A/B comparisons)
+static int g_attn_impl = 0;
 extern "C" int svla_set_attn_impl(int impl) {
   g_attn_impl = impl;
   return SVLA_OK;
@@ -305,6 +315,8 @@ extern "C" int svla_attn_fwd(svla_ctx* ctx, int mode, const void* q, const void*
     const bool tc2_ok = svla_attn_tc2_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o);
     if (tc2_ok && g_attn_impl != 1)
       return svla_attn_tc2_fwd(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, as_stream(stream));
+    if (g_attn_impl != 1 && g_attn_impl != 3 && svla_attn_ws_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o))
+      return svla_attn_ws_fwd(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, as_stream(stream));
     const bool tc_ok = svla_attn_tc_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o);
     if (g_attn_impl == 2 && !tc_ok) {
       svla_set_error("svla_attn_fwd: tcgen05 attention requested for an unsupported case (S=%d dtype=%d mode=%d)", S,
@@ -343,6 +355,9 @@ extern "C" int svla_attn_bwd(svla_ctx* ctx, int mode, const void* q, const void*
     if (grads_ok && g_attn_impl != 1 && svla_attn_tc2_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o))
       return svla_attn_tc2_bwd(ctx, mode, q, k, v, ld, o, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale,
                                as_stream(stream));
+    if (grads_ok && g_attn_impl != 1 && g_attn_impl != 3 && svla_attn_ws_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o))
+      return svla_attn_ws_bwd(ctx, mode, q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale,
+                              as_stream(stream));
     const bool tc_ok = svla_attn_tc_supported(mode, dtype, S, dh, ld, ldo, q, k, v, o) && grads_ok;
     if (g_attn_impl == 2 && !tc_ok) {
       svla_set_error("svla_attn_bwd: tcgen05 attention requested for an unsupported case (S=%d dtype=%d mode=%d)", S,

@@ -290,6 +290,50 @@ int make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, 
   return SVLA_OK;
 }
 
+// 3-D bf16 tensor map over [d2][d1][d0] (d0 contiguous; row stride ld1 elements, d2 stride d1 * ld1), box {b0, b1, 1}, 128B
+// swizzle.  The attention kernels address a (sequence, head) tile as (head * 64, 0, sequence): rows beyond the
+// sequence (d1) are zero-filled on loads and clipped on stores instead of touching the neighbouring sequence.
+int make_tmap3(svla_ctx* ctx, const void* ptr, long long d0, long long d1, long long d2, long long ld1, int b0, int b1,
+               CUtensorMap* out) {
+  if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
+  TmapCache* tc = reinterpret_cast<TmapCache*>(ctx->tmap_cache);
+  if (d1 >= 4096) {
+    svla_set_error("make_tmap3: sequence extent %lld too large", d1);
+    return SVLA_ERR_BAD_ARG;
+  }
+  const long long ld2 = d1 * ld1;  // sequences are stored back to back
+  const auto key = std::make_tuple(ptr, d0 * 4096 + d1, d2, ld1, b0, b1, 3);
+  {
+    std::lock_guard<std::mutex> lk(tc->mu);
+    auto it = tc->maps.find(key);
+    if (it != tc->maps.end()) {
+      *out = it->second;
+      return SVLA_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    svla_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SVLA_ERR_INTERNAL;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld1 * 2, (cuuint64_t)ld2 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    svla_set_error("cuTensorMapEncodeTiled (3-D) failed (%d): ptr=%p dims=%lld x %lld x %lld ld=%lld,%lld box=%dx%d", (int)r,
+                   ptr, d0, d1, d2, ld1, ld2, b0, b1);
+    return SVLA_ERR_INTERNAL;
+  }
+  std::lock_guard<std::mutex> lk(tc->mu);
+  if (tc->maps.size() > 8192) tc->maps.clear();
+  tc->maps[key] = *out;
+  return SVLA_OK;
+}
+
 template <int BN, bool AMN, bool BMN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mc2, const TcArgs& g,
               int grid, cudaStream_t st) {
@@ -315,6 +359,10 @@ void svla_tmap_cache_free(void* cache) { delete reinterpret_cast<TmapCache*>(cac
 int svla_make_tmap_bf16(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
                         CUtensorMap* out) {
   return make_tmap(ctx, ptr, inner, outer, ld, bi, bo, out);
+}
+int svla_make_tmap3_bf16(svla_ctx* ctx, const void* ptr, long long d0, long long d1, long long d2, long long ld1, int b0,
+                         int b1, CUtensorMap* out) {
+  return make_tmap3(ctx, ptr, d0, d1, d2, ld1, b0, b1, out);
 }
 int svla_make_tmap(svla_ctx* ctx, const void* ptr, long long inner, long long outer, long long ld, int bi, int bo,
                    CUtensorMap* out, int kind) {

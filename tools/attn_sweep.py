@@ -4,7 +4,11 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from safevla_b200 import ops
+from safevla_b200 import _lib
 dev = torch.device("cuda:0"); bf = torch.bfloat16
+# SVLA_ATTN_IMPL: 0 = default (warp-specialised kernels for S <= 128), 3 = the round-1 one-CTA-per-item kernels
+_lib.load_library().svla_set_attn_impl(int(os.environ.get("SVLA_ATTN_IMPL", "0")))
+print("attention impl", os.environ.get("SVLA_ATTN_IMPL", "0"))
 
 def t_of(fn, n=8):
     for _ in range(3):
@@ -14,9 +18,9 @@ def t_of(fn, n=8):
     for i in range(n):
         fn(); e[i + 1].record()
     torch.cuda.synchronize()
-    return min(e[i].elapsed_time(e[i + 1]) for i in range(n)) * 1e-3
+    return sum(e[i].elapsed_time(e[i + 1]) for i in range(n)) / n * 1e-3
 
-for mode, B, S in ((0, 4096, 117), (0, 1024, 117), (0, 2048, 201), (1, 64, 128), (1, 8, 256)):
+for mode, B, S in ((0, 4096, 117), (0, 1024, 117), (0, 4096, 128), (0, 2048, 201), (1, 64, 128), (1, 1024, 128), (1, 8, 256)):
     D, H = 512, 8
     qkv = torch.randn(B * S, 3 * D, device=dev, dtype=bf) * 0.5
     o, do = torch.empty(B * S, D, device=dev, dtype=bf), torch.randn(B * S, D, device=dev, dtype=bf)
