@@ -304,6 +304,19 @@ int svla_scale_by(svla_ctx* ctx, float* x, long long n, const float* scale_dev, 
 /* fp32 -> bf16 cast of a flat buffer (parameter shadow) */
 int svla_cast_bf16(svla_ctx* ctx, const float* x, void* y, long long n, svla_stream stream);
 
+/* Attention of the parity-grade tensor-core mode (S <= 128, head dim 64, modes FULL / TRAJ_CAUSAL): q / k / v (and
+ * d_o) are (hi, lo) bf16 pairs of the fp32 tensors as svla_split_concat(axis 1, pattern {0, 1}) writes them -- the
+ * `_hi` pointer addresses head 0 of the hi half, the lo half starts `lo_off` elements further on the same row (row
+ * stride ld) -- every product runs as hi*hi + lo*hi + hi*lo on the tcgen05 kernels, P / dS are split in registers;
+ * outputs (o, dq, dk, dv) and lse are fp32.  Same semantics as svla_attn_fwd / svla_attn_bwd otherwise. */
+int svla_attn_split_fwd(svla_ctx* ctx, int mode, const void* q_hi, const void* k_hi, const void* v_hi, long long lo_off,
+                        long long ld, float* o, long long ldo, float* lse, const int64_t* traj, int B, int S, int H,
+                        int dh, float scale, svla_stream stream);
+int svla_attn_split_bwd(svla_ctx* ctx, int mode, const void* q_hi, const void* k_hi, const void* v_hi, long long lo_off,
+                        long long ld, const void* do_hi, long long do_lo_off, long long lddo, float* dq, float* dk,
+                        float* dv, long long ldd, const float* lse, const int64_t* traj, int B, int S, int H, int dh,
+                        float scale, svla_stream stream);
+
 /* Split-operand staging of the parity-grade tensor-core mode (precision "bf16x3" / "bf16x6"): x fp32 [rows, cols]
  * (row stride ldx) is decomposed into bf16 parts p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) and the parts
  * named by pattern[0..nprod) are concatenated along the contraction dimension of the GEMM operand the tensor will be:

@@ -107,6 +107,10 @@ PROTOTYPES: Dict[str, list] = {
     "svla_fill_rows": [c_p, c_p, c_p, C.c_int, c_ll, RowMap, c_ll, C.c_int, c_p],
     "svla_scale_by": [c_p, c_p, c_ll, c_p, c_p],
     "svla_cast_bf16": [c_p, c_p, c_p, c_ll, c_p],
+    "svla_attn_split_fwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_ll, c_p, c_ll, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                            C.c_float, c_p],
+    "svla_attn_split_bwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_p, c_p, c_p, c_ll, c_p, c_p,
+                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
     "svla_split_concat": [c_p, c_p, c_ll, c_ll, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.POINTER(C.c_int), c_p],
     "svla_hash_rows": [c_p, c_p, c_ll, C.c_int, c_p, c_p],
     "svla_episode_cost_step": [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p],

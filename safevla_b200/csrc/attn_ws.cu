@@ -542,6 +542,250 @@ int launch_bwd(const WsMaps& m, const WsArgs& a, int grid, cudaStream_t st) {
   return SVLA_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------ backward, split operands
+// Parity-grade variant (NP = 3): Q, K, V, dO arrive as (hi, lo) bf16 pairs (8 tiles = 128 KB, one stage), every product
+// is hi*hi + lo*hi + hi*lo.  P (hi, lo) and dS (hi, lo) take turns in ONE 64 KB buffer: P -> dV = P^T dO retires -> dS
+// (kept in registers meanwhile) -> dK = dS^T Q, dQ = dS K.  fp32 gradients out.
+template <int MODE>
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_x3_kernel(const __grid_constant__ WsMaps m, WsArgs a) {
+  constexpr uint32_t kStage = 8 * kTile;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sPB = smem + kStage;       // 64 KB: P hi | P lo, then dS hi | dS lo
+  int* sTraj = reinterpret_cast<int*>(sPB + 4 * kTile);          // [buffer 2][128]
+  float* sDelta = reinterpret_cast<float*>(sTraj + 256);          // [buffer 2][half 2][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sDelta + 512);
+  uint64_t* empty = full + 1;
+  uint64_t* sdp_full = empty + 1;     // [2]
+  uint64_t* out_full = sdp_full + 2;  // [2]
+  uint64_t* out_free = out_full + 2;  // [2]
+  uint64_t* p_full = out_free + 2;    // P written
+  uint64_t* dv_done = p_full + 1;     // dV MMAs retired: the buffer may take dS
+  uint64_t* ds_full = dv_done + 1;    // dS written
+  uint64_t* pb_free = ds_full + 1;    // dK / dQ MMAs retired: the buffer may take the next item's P
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pb_free + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(full, 1);
+    mbar_init(empty, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&sdp_full[t], 1);
+      mbar_init(&out_full[t], 1);
+      mbar_init(&out_free[t], 128);
+    }
+    mbar_init(p_full, 256);
+    mbar_init(dv_done, 1);
+    mbar_init(ds_full, 256);
+    mbar_init(pb_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const int S = a.S, H = a.H;
+  const int total = a.B * H;
+  const int n_items = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp < 4) {
+    reg_dec<56>();
+    if (warp == 0) {
+      if (elect_one()) {
+        for (int it = 0; it < n_items; ++it) {
+          const int w = blockIdx.x + it * gridDim.x, b = w / H, h = w % H;
+          mbar_wait(empty, (it & 1) ^ 1);
+          mbar_expect_tx(full, kStage);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            tma_load_3d(smem + p * kTile, &m.q[p], full, h * DH, 0, b);
+            tma_load_3d(smem + (2 + p) * kTile, &m.k[p], full, h * DH, 0, b);
+            tma_load_3d(smem + (4 + p) * kTile, &m.v[p], full, h * DH, 0, b);
+            tma_load_3d(smem + (6 + p) * kTile, &m.d[p], full, h * DH, 0, b);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t q = smem_u32(smem), k = q + 2 * kTile, v = q + 4 * kTile, d = q + 6 * kTile, pb = smem_u32(sPB);
+      for (int it = 0; it < n_items; ++it) {
+        const int t = it & 1;
+        const uint32_t tb = tmem + t * 256;
+        mbar_wait(full, it & 1);
+        mbar_wait(&out_free[t], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {  // S = Q K^T
+            const uint32_t xa = q + (pr == 1 ? kTile : 0), xb = k + (pr == 2 ? kTile : 0);
+#pragma unroll
+            for (int kk = 0; kk < DH / 16; ++kk)
+              umma_bf16(tb, desc_kmajor(xa, kk), desc_kmajor(xb, kk), idesc(128, 128, false, false), (pr > 0 || kk > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {  // dP = dO V^T
+            const uint32_t xa = d + (pr == 1 ? kTile : 0), xb = v + (pr == 2 ? kTile : 0);
+#pragma unroll
+            for (int kk = 0; kk < DH / 16; ++kk)
+              umma_bf16(tb + 128, desc_kmajor(xa, kk), desc_kmajor(xb, kk), idesc(128, 128, false, false), (pr > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&sdp_full[t]);
+        }
+        __syncwarp();
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {  // dV[keys, dh] = P^T dO
+            const uint32_t xa = pb + (pr == 1 ? 2 * kTile : 0), xb = d + (pr == 2 ? kTile : 0);
+#pragma unroll
+            for (int kk = 0; kk < TS / 16; ++kk)
+              umma_bf16(tb, desc_p_mnmajor(xa, kk), desc_mnmajor64(xb, kk), idesc(128, 64, true, true), (pr > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(dv_done);
+        }
+        __syncwarp();
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {  // dK[keys, dh] = dS^T Q
+            const uint32_t xa = pb + (pr == 1 ? 2 * kTile : 0), xb = q + (pr == 2 ? kTile : 0);
+#pragma unroll
+            for (int kk = 0; kk < TS / 16; ++kk)
+              umma_bf16(tb + 64, desc_p_mnmajor(xa, kk), desc_mnmajor64(xb, kk), idesc(128, 64, true, true), (pr > 0 || kk > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {  // dQ[queries, dh] = dS K
+            const uint32_t xa = pb + (pr == 1 ? 2 * kTile : 0), xb = k + (pr == 2 ? kTile : 0);
+#pragma unroll
+            for (int kk = 0; kk < TS / 16; ++kk)
+              umma_bf16(tb + 128, desc_p_kmajor(xa, kk), desc_mnmajor64(xb, kk), idesc(128, 64, false, true), (pr > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&out_full[t]);
+          umma_commit(pb_free);
+          umma_commit(empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 12) {
+    reg_inc<176>();
+    const int i = ((warp & 3) << 5) + lane;
+    const int hf = (warp - 4) >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float sl2 = a.scale * kLog2e;
+    for (int it = 0; it < n_items; ++it) {
+      const int w = blockIdx.x + it * gridDim.x, b = w / H, h = w % H, t = it & 1;
+      const long long row0 = (long long)b * S;
+      const int* traj = sTraj + t * 128;
+      if (MODE == SVLA_ATTN_TRAJ_CAUSAL && hf == 0) sTraj[t * 128 + i] = (i < S) ? (int)a.traj[row0 + i] : -1 - i;
+      const float lse2 = (i < S) ? a.lse[((long long)b * H + h) * S + i] * kLog2e : 0.f;
+      mbar_wait(&sdp_full[t], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tb = tmem + lane_base + t * 256 + hf * 64;
+      uint32_t rs[64], rp[64];
+      tmem_ld32(tb, rs);
+      tmem_ld32(tb + 32, rs + 32);
+      tmem_ld32(tb + 128, rp);
+      tmem_ld32(tb + 160, rp + 32);
+      if (MODE == SVLA_ATTN_TRAJ_CAUSAL) named_bar_sync(1, 256);
+      tmem_wait_ld();
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
+      const int my_traj = (MODE == SVLA_ATTN_TRAJ_CAUSAL) ? traj[i] : 0;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) {
+        const int col = hf * 64 + e;
+        bool ok = col < S;
+        if (MODE == SVLA_ATTN_TRAJ_CAUSAL) ok = col <= i && traj[col] == my_traj && i < S;
+        const float p = ok ? ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
+        rs[e] = __float_as_uint(p);
+        d4[e & 3] = fmaf(p, __uint_as_float(rp[e]), d4[e & 3]);
+      }
+      float* sd = sDelta + t * 256;
+      sd[hf * 128 + i] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+      named_bar_sync(2, 256);
+      const float delta = sd[i] + sd[128 + i];
+      mbar_wait(pb_free, (it & 1) ^ 1);
+#pragma unroll
+      for (int l8 = 0; l8 < 8; ++l8) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] = __uint_as_float(rs[l8 * 8 + e]);
+        store_p8_parts<3>(sPB, i, hf * 8 + l8, p);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive_release(p_full);
+      // dS = P (dP - delta), in place of dP, while dV = P^T dO runs
+#pragma unroll
+      for (int e = 0; e < 64; ++e) rp[e] = __float_as_uint(__uint_as_float(rs[e]) * (__uint_as_float(rp[e]) - delta));
+      mbar_wait(dv_done, it & 1);
+#pragma unroll
+      for (int l8 = 0; l8 < 8; ++l8) {
+        float ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ds[e] = __uint_as_float(rp[l8 * 8 + e]);
+        store_p8_parts<3>(sPB, i, hf * 8 + l8, ds);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive_release(ds_full);
+    }
+  } else {
+    reg_dec<104>();
+    const int i = ((warp & 3) << 5) + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int it = 0; it < n_items; ++it) {
+      const int w = blockIdx.x + it * gridDim.x, b = w / H, h = w % H, t = it & 1;
+      const long long orow = ((long long)b * S + i) * a.ldd + h * DH;
+      mbar_wait(&out_full[t], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tb = tmem + lane_base + t * 256;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tb, r0);
+      tmem_ld32(tb + 32, r1);
+      tmem_wait_ld();
+      if (i < S) store_out_row64<3>(a.dv, orow, r0, r1, 1.f);
+      tmem_ld32(tb + 64, r0);
+      tmem_ld32(tb + 96, r1);
+      tmem_wait_ld();
+      if (i < S) store_out_row64<3>(a.dk, orow, r0, r1, a.scale);
+      tmem_ld32(tb + 128, r0);
+      tmem_ld32(tb + 160, r1);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive_release(&out_free[t]);
+      if (i < S) store_out_row64<3>(a.dq, orow, r0, r1, a.scale);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+constexpr size_t kBwdX3Smem = 8 * kTile + 4 * kTile + 1024 + 2048 + 256 + 1024;
+
+template <int MODE>
+int launch_bwd_x3(const WsMaps& m, const WsArgs& a, int grid, cudaStream_t st) {
+  auto kern = attn_ws_bwd_x3_kernel<MODE>;
+  static bool attr = false;
+  if (!attr) {
+    SVLA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdX3Smem));
+    attr = true;
+  }
+  kern<<<grid, kBwdThreads, kBwdX3Smem, st>>>(m, a);
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
+
 template <int NP> constexpr size_t fwd_smem_bytes() {
   return (size_t)(NP == 1 ? 4 : 2) * 3 * (NP == 1 ? 1 : 2) * kTile + 2048 + 256 + 1024;
 }
@@ -599,4 +843,66 @@ int svla_attn_ws_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
   const int grid = std::min(B * H, ctx->sm_count);
   if (mode == SVLA_ATTN_FULL) return launch_bwd<SVLA_ATTN_FULL>(m, a, grid, st);
   return launch_bwd<SVLA_ATTN_TRAJ_CAUSAL>(m, a, grid, st);
+}
+
+// ---- split-operand (parity-grade) entry points: x_lo = x_hi + lo_off elements (svla_split_concat, axis 1, {0, 1})
+static bool split_args_ok(int mode, int S, int dh, long long ld, long long lo_off, const void* q, const void* k,
+                          const void* v) {
+  return dh == DH && S >= 1 && S <= TS && (mode == SVLA_ATTN_FULL || mode == SVLA_ATTN_TRAJ_CAUSAL) && ld % 8 == 0 &&
+         lo_off % 8 == 0 && al16(q) && al16(k) && al16(v);
+}
+
+extern "C" int svla_attn_split_fwd(svla_ctx* ctx, int mode, const void* q_hi, const void* k_hi, const void* v_hi,
+                                   long long lo_off, long long ld, float* o, long long ldo, float* lse,
+                                   const int64_t* traj, int B, int S, int H, int dh, float scale, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && q_hi && k_hi && v_hi && o, "NULL argument");
+  SVLA_CHECK_ARG(split_args_ok(mode, S, dh, ld, lo_off, q_hi, k_hi, v_hi) && ldo % 4 == 0 && al16(o),
+                 "split attention: S <= 128, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
+  SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
+  if (B <= 0) return SVLA_OK;
+  WsMaps m{};
+  int rc;
+  const __nv_bfloat16* qs[2] = {reinterpret_cast<const __nv_bfloat16*>(q_hi), reinterpret_cast<const __nv_bfloat16*>(q_hi) + lo_off};
+  const __nv_bfloat16* ks[2] = {reinterpret_cast<const __nv_bfloat16*>(k_hi), reinterpret_cast<const __nv_bfloat16*>(k_hi) + lo_off};
+  const __nv_bfloat16* vs[2] = {reinterpret_cast<const __nv_bfloat16*>(v_hi), reinterpret_cast<const __nv_bfloat16*>(v_hi) + lo_off};
+  for (int p = 0; p < 2; ++p) {
+    if ((rc = svla_make_tmap3_bf16(ctx, qs[p], (long long)H * DH, S, B, ld, DH, TS, &m.q[p]))) return rc;
+    if ((rc = svla_make_tmap3_bf16(ctx, ks[p], (long long)H * DH, S, B, ld, DH, TS, &m.k[p]))) return rc;
+    if ((rc = svla_make_tmap3_bf16(ctx, vs[p], (long long)H * DH, S, B, ld, DH, TS, &m.v[p]))) return rc;
+  }
+  WsArgs a{};
+  a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = lse; a.o = o; a.ldo = ldo;
+  const int grid = std::min(B * H, ctx->sm_count);
+  if (mode == SVLA_ATTN_FULL) return launch_fwd<SVLA_ATTN_FULL, 3>(m, a, grid, as_stream(stream));
+  return launch_fwd<SVLA_ATTN_TRAJ_CAUSAL, 3>(m, a, grid, as_stream(stream));
+}
+
+extern "C" int svla_attn_split_bwd(svla_ctx* ctx, int mode, const void* q_hi, const void* k_hi, const void* v_hi,
+                                   long long lo_off, long long ld, const void* do_hi, long long do_lo_off, long long lddo,
+                                   float* dq, float* dk, float* dv, long long ldd, const float* lse, const int64_t* traj,
+                                   int B, int S, int H, int dh, float scale, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && q_hi && k_hi && v_hi && do_hi && dq && dk && dv && lse, "NULL argument");
+  SVLA_CHECK_ARG(split_args_ok(mode, S, dh, ld, lo_off, q_hi, k_hi, v_hi) && lddo % 8 == 0 && do_lo_off % 8 == 0 &&
+                     al16(do_hi) && ldd % 4 == 0 && al16(dq) && al16(dk) && al16(dv),
+                 "split attention: S <= 128, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
+  SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
+  if (B <= 0) return SVLA_OK;
+  WsMaps m{};
+  int rc;
+  const __nv_bfloat16* qs[2] = {reinterpret_cast<const __nv_bfloat16*>(q_hi), reinterpret_cast<const __nv_bfloat16*>(q_hi) + lo_off};
+  const __nv_bfloat16* ks[2] = {reinterpret_cast<const __nv_bfloat16*>(k_hi), reinterpret_cast<const __nv_bfloat16*>(k_hi) + lo_off};
+  const __nv_bfloat16* vs[2] = {reinterpret_cast<const __nv_bfloat16*>(v_hi), reinterpret_cast<const __nv_bfloat16*>(v_hi) + lo_off};
+  const __nv_bfloat16* ds[2] = {reinterpret_cast<const __nv_bfloat16*>(do_hi), reinterpret_cast<const __nv_bfloat16*>(do_hi) + do_lo_off};
+  for (int p = 0; p < 2; ++p) {
+    if ((rc = svla_make_tmap3_bf16(ctx, qs[p], (long long)H * DH, S, B, ld, DH, TS, &m.q[p]))) return rc;
+    if ((rc = svla_make_tmap3_bf16(ctx, ks[p], (long long)H * DH, S, B, ld, DH, TS, &m.k[p]))) return rc;
+    if ((rc = svla_make_tmap3_bf16(ctx, vs[p], (long long)H * DH, S, B, ld, DH, TS, &m.v[p]))) return rc;
+    if ((rc = svla_make_tmap3_bf16(ctx, ds[p], (long long)H * DH, S, B, lddo, DH, TS, &m.d[p]))) return rc;
+  }
+  WsArgs a{};
+  a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = const_cast<float*>(lse);
+  a.dq = dq; a.dk = dk; a.dv = dv; a.ldd = ldd;
+  const int grid = std::min(B * H, ctx->sm_count);
+  if (mode == SVLA_ATTN_FULL) return launch_bwd_x3<SVLA_ATTN_FULL>(m, a, grid, as_stream(stream));
+  return launch_bwd_x3<SVLA_ATTN_TRAJ_CAUSAL>(m, a, grid, as_stream(stream));
 }

@@ -336,9 +336,38 @@ def _timed(which: str, flops: float, meta, launch):
     PROFILE.setdefault(which, []).append((flops, e0, e1, meta))
 
 
-def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bias=None, keymask=None):
-    """q/k/v: 2-D views [B*S, >=H*dh] sharing one row stride (e.g. column slices of a packed qkv buffer)."""
+def _split_qkv(q, k, v, H, dh):
+    """(hi, lo) bf16 staging of fp32 q / k / v column views for svla_attn_split_*: returns (buffer, q_hi, k_hi, v_hi
+    views' element offsets, lo_off, ld).  One staging launch when the three views are adjacent columns of one buffer."""
+    D, rows, ld = H * dh, q.shape[0], q.stride(0)
+    if k.data_ptr() == q.data_ptr() + 4 * D and v.data_ptr() == q.data_ptr() + 8 * D:
+        buf = split_concat(q, ld, rows, 3 * D, 1, (0, 1))  # [rows, 6D]: hi q|k|v, lo q|k|v
+        return buf, (0, D, 2 * D), 3 * D, 6 * D
+    buf = torch.empty(rows, 6 * D, device=q.device, dtype=torch.bfloat16)
+    pat = (C.c_int * 2)(0, 1)
+    for j, x in enumerate((q, k, v)):  # [hi | lo] pairs side by side: lo_off = D
+        check(_lib().svla_split_concat(get_ctx(), ptr(x), x.stride(0), rows, D, buf.data_ptr() + 2 * (2 * j * D),
+                                       6 * D, 1, 2, pat, stream_ptr()), "svla_split_concat")
+    return buf, (0, 2 * D, 4 * D), D, 6 * D
+
+
+def _use_split_attn(split, q, mode, S, dh):
+    return bool(split) and q.dtype == torch.float32 and S <= 128 and dh == 64 and mode in (L.ATTN_FULL, L.ATTN_TRAJ_CAUSAL)
+
+
+def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bias=None, keymask=None, split=0):
+    """q/k/v: 2-D views [B*S, >=H*dh] sharing one row stride (e.g. column slices of a packed qkv buffer).
+    split != 0 with fp32 tensors (parity-grade tensor-core mode): the products run as split-bf16 sums on the tcgen05
+    kernel (svla_attn_split_fwd) instead of the fp32 CUDA-core kernel."""
     assert q.stride(0) == k.stride(0) == v.stride(0) and q.dtype == k.dtype == v.dtype == o.dtype
+    if _use_split_attn(split, q, mode, S, dh):
+        buf, (qo, ko, vo), lo_off, ld = _split_qkv(q, k, v, H, dh)
+        base = buf.data_ptr()
+        _timed("attn_fwd", 3 * 4.0 * B * H * S * S * dh, (mode, B, S, "f32x3"), lambda: check(
+            _lib().svla_attn_split_fwd(get_ctx(), mode, base + 2 * qo, base + 2 * ko, base + 2 * vo, lo_off, ld, ptr(o),
+                                       o.stride(0), ptr(lse), ptr(traj), B, S, H, dh, scale, stream_ptr()),
+            "svla_attn_split_fwd"))
+        return o
     _timed("attn_fwd", 4.0 * B * H * S * S * dh, (mode, B, S, str(q.dtype)[6:]), lambda: check(
         _lib().svla_attn_fwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), o.stride(0), dt(q),
                              ptr(lse), ptr(traj), ptr(bias), ptr(keymask), B, S, H, dh, scale, stream_ptr()),
@@ -346,9 +375,19 @@ def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bi
     return o
 
 
-def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, traj=None):
+def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, traj=None, split=0):
     assert q.stride(0) == k.stride(0) == v.stride(0) and dq.stride(0) == dk.stride(0) == dv.stride(0)
     assert o.stride(0) == d_o.stride(0)
+    if _use_split_attn(split, q, mode, S, dh):
+        buf, (qo, ko, vo), lo_off, ld = _split_qkv(q, k, v, H, dh)
+        D = H * dh
+        dbuf = split_concat(d_o, d_o.stride(0), d_o.shape[0], D, 1, (0, 1))  # [rows, 2D]: hi | lo
+        base = buf.data_ptr()
+        _timed("attn_bwd", 3 * 10.0 * B * H * S * S * dh, (mode, B, S, "f32x3"), lambda: check(
+            _lib().svla_attn_split_bwd(get_ctx(), mode, base + 2 * qo, base + 2 * ko, base + 2 * vo, lo_off, ld,
+                                       ptr(dbuf), D, 2 * D, ptr(dq), ptr(dk), ptr(dv), dq.stride(0), ptr(lse), ptr(traj),
+                                       B, S, H, dh, scale, stream_ptr()), "svla_attn_split_bwd"))
+        return
     # five S x S x dh products: the score recompute, dP, dV, dK, dQ
     _timed("attn_bwd", 10.0 * B * H * S * S * dh, (mode, B, S, str(q.dtype)[6:]), lambda: check(
         _lib().svla_attn_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), ptr(d_o), o.stride(0),

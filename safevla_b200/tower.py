@@ -149,7 +149,7 @@ class Tower:
                 qkv = self._lin_fwd(x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", self._new(Ms, 3 * D))
                 ao, lse = self._new(Ms, D), self._new(Rc * H * S, dtype=torch.float32)
                 ops.attn_fwd(ATTN_FULL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, lse, Rc, S,
-                             scale=1.0 / math.sqrt(DH))
+                             scale=1.0 / math.sqrt(DH), split=self.split)
                 s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Ms, D),
                                    residual=x)
                 m1, r1 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
@@ -249,7 +249,7 @@ class Tower:
                 dqkv = self._new(Ms, 3 * D)
                 ops.attn_bwd(ATTN_FULL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], t[f"ao_{l}"], dao,
                              dqkv[:, 0:D], dqkv[:, D:2 * D], dqkv[:, 2 * D:3 * D], t[f"lse_{l}"], Rc, S,
-                             scale=1.0 / math.sqrt(DH))
+                             scale=1.0 / math.sqrt(DH), split=self.split)
                 dx = self._lin_bwd(dqkv, x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias",
                                    dx=self._new(Ms, D), residual=ds1)
                 del dqkv
@@ -302,7 +302,7 @@ class Tower:
             qkv = self._gemm(y1, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, 3 * D, dtype=ddt))
             ao, lse = self._new(Md, D, dtype=ddt), self._new(N * H * T, dtype=f32)
             ops.attn_fwd(ATTN_TRAJ_CAUSAL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, lse, N, T,
-                         scale=1.0 / math.sqrt(DH), traj=traj_nt)
+                         scale=1.0 / math.sqrt(DH), traj=traj_nt, split=self.split)
             h2 = self._gemm(ao, W.w(p + "attention.wo.weight", dtype=ddt), self._new(Md, D, dtype=f32), residual=h)
             r2 = self._new(Md, dtype=f32)
             y2 = ops.rmsnorm_fwd(h2, W.p(p + "ffn_norm.weight"), self._new(Md, D, dtype=ddt), RMS_EPS, r2)
@@ -416,7 +416,7 @@ class Tower:
             dqkv = self._new(Md, 3 * D, dtype=ddt)
             ops.attn_bwd(ATTN_TRAJ_CAUSAL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, dao, dqkv[:, 0:D],
                          dqkv[:, D:2 * D], dqkv[:, 2 * D:3 * D], t[f"lse_{l}"], N, T, scale=1.0 / math.sqrt(DH),
-                         traj=traj_nt)
+                         traj=traj_nt, split=self.split)
             self._gemm(dqkv, t[f"y1_{l}"], W.g(p + "attention.wq.weight", (3 * D, D), 3), trans_a=True, trans_b=False,
                      accumulate=True)
             dy1 = self._gemm(dqkv, W.w(p + "attention.wq.weight", (3 * D, D), 3, dtype=ddt), self._new(Md, D, dtype=ddt),

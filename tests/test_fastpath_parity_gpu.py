@@ -28,15 +28,21 @@ REPORT = os.path.join(ROOT, "gpurun_out", "fastpath_parity.json")
 
 # relative tolerances (max |err| / max |ref|) per precision:
 #   fwd   logits / log-probs / values / cost values          loss  the four loss scalars
-#   gnorm every parameter-gradient L2 norm                    grad  the ten full gradient tensors
-# fp32 and bf16x3 meet BASELINE's 1e-4 gate; bf16 rounds every GEMM operand to 8 mantissa bits (2^-9 relative).
+#   gnorm every parameter-gradient L2 norm                    grad  the ten full gradient tensors, element-wise
+#   cos   cosine similarity of each full gradient tensor with the reference's, cos_all of their concatenation
+# fp32 and bf16x3 meet BASELINE's 1e-4 gate on logits / values / losses.  Measured on B200 (gpurun_out/
+# fastpath_parity.json, worst of the three goldens): fp32 1.8e-6 / 5e-7 / 7e-5 / 2.6e-5; bf16x3 1.8e-5 / 2.5e-6 /
+# 1.0e-4 / 1.0e-2; bf16 2.4e-2 / 7.4e-4 / 9.6e-3 / 6.4e-2.  The element-wise gradient bound of the non-bit-exact modes
+# is set by ReLU-boundary flips: a pre-activation within the forward error of zero flips its mask, which moves ONE
+# element of a column-sum gradient (LayerNorm / bias gradients) by a whole summand -- the 1e-2 outlier of bf16x3 is
+# `visual_encoder.text_adapter.1.bias` at cosine 0.9999975; any implementation that is not bit-identical to the
+# reference shows it, so those tensors are held to the direction (cos) as well.
 TOL = {
-    "fp32": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3),
-    "bf16x3": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3),
-    "bf16x6": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3),
-    # bf16: a 128-row batch does not average the operand rounding out; nearly-cancelling sums (the actor bias gradient =
-    # column sum of d loss / d logits) are judged by direction (`cos`, cosine similarity with the reference gradient)
-    "bf16": dict(fwd=3e-2, loss=2e-2, gnorm=0.15, grad=None, cos=0.97, cos_all=0.995),
+    "fp32": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=2e-3, cos=0.999999, cos_all=0.9999999),
+    "bf16x3": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=3e-2, cos=0.99999, cos_all=0.999999),
+    "bf16x6": dict(fwd=1e-4, loss=1e-4, gnorm=2e-3, grad=3e-2, cos=0.99999, cos_all=0.999999),
+    # bf16 rounds every GEMM operand to 8 mantissa bits (2^-9 relative)
+    "bf16": dict(fwd=4e-2, loss=2e-3, gnorm=3e-2, grad=0.15, cos=0.999, cos_all=0.9999),
 }
 
 
@@ -124,18 +130,17 @@ def test_reference_golden_every_precision(dev, name, precision):
     for k in ("ppo_total", "value", "action", "entropy"):
         assert rec["loss_" + k] < tol["loss"], (k, rec)
     assert rec["grad_norm_worst"] < tol["gnorm"], rec
-    if tol["grad"] is not None:
-        assert rec["grad_full_worst"] < tol["grad"], rec
-    else:
-        assert rec["grad_cos_worst"] > tol["cos"] and rec["grad_cos_all"] > tol["cos_all"], rec
+    assert rec["grad_full_worst"] < tol["grad"], rec
+    assert rec["grad_cos_worst"] > tol["cos"] and rec["grad_cos_all"] > tol["cos_all"], rec
 
 
-@pytest.mark.parametrize("precision,tol_delta,tol_lam", [("bf16x3", 2e-3, 1e-5), ("bf16", 0.25, 1e-5)])
+@pytest.mark.parametrize("precision,tol_delta,tol_lam", [("bf16x3", 1e-3, 1e-5), ("bf16", 0.06, 1e-5)])
 def test_whole_update_fast_modes_vs_oracle(dev, precision, tol_delta, tol_lam):
     """PPOLagUpdater.update (GAE -> 2 x [3-tower fwd, fused loss, bwd, clip, Adam] -> lambda) in the tensor-core modes
     against the CPU oracle.  The comparison is on the parameter MOVEMENT (Adam's first steps are sign-like, so the
     movement is O(lr) per element and an operand-rounding error shows up as a fraction of it):
-        max |delta_mine - delta_ref| / max |delta_ref| ,   the loss of the last repeat,   lambda."""
+        || delta_mine - delta_ref ||_2 / || delta_ref ||_2  (measured: bf16x3 1.9e-4, bf16 1.9e-2),
+        the loss of the last repeat (3.7e-6 / 1.3e-4),   lambda (exact: it only sees the episode costs)."""
     from oracle.update_oracle import oracle_update
     from safevla_b200.model import B200SafeActorCritic
     from safevla_b200.storage import B200RolloutStorage
@@ -167,7 +172,7 @@ def test_whole_update_fast_modes_vs_oracle(dev, precision, tol_delta, tol_lam):
     _report(f"update/{precision}", rec)
     assert den > 5e-4
     assert rec["lambda_abs"] < tol_lam, rec
-    assert rec["loss_rel"] < (1e-4 if precision != "bf16" else 2e-2), rec
+    assert rec["loss_rel"] < (1e-4 if precision != "bf16" else 2e-3), rec
     assert rec["delta_l2_rel"] < tol_delta, rec
 
 
@@ -203,5 +208,6 @@ def test_cfg2_bench_rollout_sampler_columns_vs_oracle(dev):
         p_ref = torch.softmax(ref["logits"], -1)
         rec[f"tv_col{col}"] = 0.5 * (p_mine - p_ref).abs().sum(-1).max().item()
     _report("cfg2_bench_rollout/bf16", rec)
+    # measured: logits 5.9e-3, values 1.6e-2, cost values 7.5e-3, total variation 2.1e-5
     for k, v in rec.items():
-        assert v < (3e-2 if not k.startswith("tv") else 1e-2), (k, rec)
+        assert v < (4e-2 if not k.startswith("tv") else 5e-4), (k, rec)
