@@ -35,6 +35,11 @@ CASES = {
 ORACLE_ONLY_CASES = {
     "T128_N1_A20_C1": dict(T=128, N=1, A=20, C=1, end_prob=1 / 40, wseed=13, rseed=777, lam=0.2),
 }
+# critic_type="discrete": HL-Gauss DiscreteCriticHead in every tower, SafePPOLogGrad(discrete_critics=True)
+# (allenact_dino_transformer.py:152-159,434-439,743-766; customized_loss.py:364-370)
+DISCRETE_CASES = {
+    "disc_T10_N2_A6_C1": dict(T=10, N=2, A=6, C=1, end_prob=1 / 5, wseed=14, rseed=555, lam=0.3, critic_type="discrete"),
+}
 FULL_GRADS = ["actor.linear.weight", "actor.linear.bias", "critic_tsfm.critic.fc.weight",
               "visual_encoder.fusion_token", "last_actions_embed.weight",
               "critic_tsfm.visual_encoder.visual_sensor_token_raw_navigation_camera",
@@ -62,12 +67,13 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref_loss, _, _ = ref_shim.reference_modules()
     only = set(sys.argv[1:])
-    for name, case in {**CASES, **ORACLE_ONLY_CASES}.items():
+    for name, case in {**CASES, **ORACLE_ONLY_CASES, **DISCRETE_CASES}.items():
         if only and name not in only:
             continue
         T, N, A, C = case["T"], case["N"], case["A"], case["C"]
-        sd = init_state_dict(A, C, case["wseed"], actor_gain=1.0)
-        model = ref_shim.build_reference_model(A, C, seed=0, num_samplers=N)
+        ctype = case.get("critic_type", "linear")
+        sd = init_state_dict(A, C, case["wseed"], actor_gain=1.0, critic_type=ctype)
+        model = ref_shim.build_reference_model(A, C, seed=0, num_samplers=N, critic_type=ctype)
         missing = model.load_state_dict(sd, strict=True)
         spec, ro, extra = build_inputs(case)
         obs = {k: v[:-1] for k, v in ro["observations"].items()}
@@ -97,7 +103,7 @@ def main():
                  "c_adv_targ": cadv, "values": extra["value_preds"][:-1], "returns": ret[:-1]}
         loss_fn = ref_loss.SafePPOLogGrad(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.01,
                                           use_clipped_value_loss=False, action_loss_schedule=None,
-                                          discrete_critics=False, normalize_advantage=False)
+                                          discrete_critics=(ctype == "discrete"), normalize_advantage=False)
         total, info = loss_fn.loss(step_count=0, batch=batch, actor_critic_output=out,
                                    lagrangian_multiplier=torch.tensor(case["lam"]))
         total.backward()
@@ -110,8 +116,20 @@ def main():
             "dlogits": logits.grad.clone(),
             "grad_norms": {k: (p.grad.norm().item() if p.grad is not None else None)
                            for k, p in model.named_parameters() if "text_encoder" not in k},
-            "grads": {k: dict(model.named_parameters())[k].grad.clone() for k in FULL_GRADS},
+            "grads": {k: p.grad.clone() for k, p in model.named_parameters()
+                      if p.grad is not None and (k in FULL_GRADS or ".critic.fc." in k)},
         }
+        if ctype == "discrete":
+            gold["full_logits"] = out.extras["full_logits"].detach().clone()
+            with torch.no_grad():
+                mine = TO.safe_model_forward(sd, obs, prev, masks, A, C)
+            for k in ("logits", "values", "c_values", "full_logits"):
+                err = (mine[k] - gold[k]).abs().max().item()
+                print(f"{name}: oracle vs reference {k}: max abs err {err:.3e}")
+                assert err < 2e-5, (k, err)
+            torch.save(gold, os.path.join(GOLDEN_DIR, name + ".pt"))
+            print(f"wrote {name}.pt  loss={float(total):.6f}")
+            continue
         # lambda == 0 KAT: SafePPOLogGrad == PPOLogGrad bit-for-bit
         out = fwd()
         t0, _ = loss_fn.loss(0, batch, out, lagrangian_multiplier=torch.tensor(0.0))

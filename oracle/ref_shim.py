@@ -293,7 +293,7 @@ def reference_modules():
 
 
 def build_reference_model(num_actions: int, num_cameras: int, seed: int, max_steps: int = 500,
-                          num_samplers: int = 1, dropout_off: bool = True):
+                          num_samplers: int = 1, dropout_off: bool = True, critic_type: str = "linear"):
     """SafeDinoLLAMATxNavActorCriticSeparate with the kwargs of
     training/online/dinov2_vits_tsfm_base.py:233-270 (C = 1 drops the manipulation camera
     and the in-hand sensor, as `full_sensor=False` does at :225-231)."""
@@ -321,6 +321,7 @@ def build_reference_model(num_actions: int, num_cameras: int, seed: int, max_ste
             initial_tgt_cache_shape=(max_steps, num_samplers, 512),
             traj_idx_uuid="traj_index", traj_max_idx=2048,
             relevant_object_box_uuid=None, accurate_object_box_uuid=None, prev_checkpoint=None,
+            critic_type=critic_type,
         )
     if dropout_off:
         # parity setting: the model forces train(); switch every Dropout off instead

@@ -125,23 +125,30 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(AttnArgs a) {
 // Backward.  Phase A (key ownership): dK_j, dV_j.  Phase B (query ownership): dQ_i.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
+  // Two [S, 64] tiles are resident at a time: phase A (one key per warp) needs Q and dO of every query plus ONE row of
+  // K and V per warp; phase B (one query per warp) needs K and V of every key plus ONE row of Q and dO per warp.  With
+  // all four tiles resident fp32 stopped at S = 208; this way S = 256 (the 256-step decoder window of BASELINE config
+  // 4) fits in fp32 as well.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int LDS = DH + Pad<T>::v;
   const int S = a.S, b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  T* sQ = reinterpret_cast<T*>(smem_raw);
-  T* sK = sQ + S * LDS;
-  T* sV = sK + S * LDS;
-  T* sdO = sV + S * LDS;
-  float* sLse = reinterpret_cast<float*>(sdO + S * LDS);  // [S]
+  T* sT0 = reinterpret_cast<T*>(smem_raw);      // phase A: Q, phase B: K
+  T* sT1 = sT0 + S * LDS;                       // phase A: dO, phase B: V
+  float* sLse = reinterpret_cast<float*>(sT1 + S * LDS);  // [S]
   float* sDelta = sLse + S;                                                    // [S]
   float* sBufA = sDelta + S;                                                   // [4][S]  p column / dS row
   float* sBufB = sBufA + 4 * S;                                                // [4][S]  dS column
-  int* sTraj = reinterpret_cast<int*>(sBufB + 4 * S);                          // [S]
+  float* sRow = sBufB + 4 * S;                                                 // [4][2][64] per-warp row pair
+  int* sTraj = reinterpret_cast<int*>(sRow + 4 * 2 * DH);                      // [S]
   const long long row0 = (long long)b * S;
-  load_head<T>(sQ, reinterpret_cast<const T*>(a.q) + row0 * a.ld + h * DH, a.ld, S, LDS);
-  load_head<T>(sK, reinterpret_cast<const T*>(a.k) + row0 * a.ld + h * DH, a.ld, S, LDS);
-  load_head<T>(sV, reinterpret_cast<const T*>(a.v) + row0 * a.ld + h * DH, a.ld, S, LDS);
-  load_head<T>(sdO, reinterpret_cast<const T*>(a.d_o) + row0 * a.ldo + h * DH, a.ldo, S, LDS);
+  const T* gq = reinterpret_cast<const T*>(a.q) + row0 * a.ld + h * DH;
+  const T* gk = reinterpret_cast<const T*>(a.k) + row0 * a.ld + h * DH;
+  const T* gv = reinterpret_cast<const T*>(a.v) + row0 * a.ld + h * DH;
+  const T* gdo = reinterpret_cast<const T*>(a.d_o) + row0 * a.ldo + h * DH;
+  T* sQ = sT0;
+  T* sdO = sT1;
+  load_head<T>(sQ, gq, a.ld, S, LDS);
+  load_head<T>(sdO, gdo, a.ldo, S, LDS);
   if (a.mode == SVLA_ATTN_TRAJ_CAUSAL)
     for (int i = threadIdx.x; i < S; i += kThreads) sTraj[i] = (int)a.traj[row0 + i];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -161,8 +168,15 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
   const int nch = (S + 31) / 32;
   float* colP = sBufA + w * S;
   float* colDS = sBufB + w * S;
+  float* rowA = sRow + w * 2 * DH;  // K_j (phase A) / Q_i (phase B)
+  float* rowB = rowA + DH;          // V_j (phase A) / dO_i (phase B)
   // ---- phase A: each warp owns keys j = w, w+4, ...
   for (int j = w; j < S; j += 4) {
+    __syncwarp();
+    rowA[lane] = to_f<T>(gk[(long long)j * a.ld + lane]);
+    rowA[lane + 32] = to_f<T>(gk[(long long)j * a.ld + lane + 32]);
+    rowB[lane] = to_f<T>(gv[(long long)j * a.ld + lane]);
+    rowB[lane + 32] = to_f<T>(gv[(long long)j * a.ld + lane + 32]);
     __syncwarp();
     for (int c = 0; c < nch; ++c) {
       const int i = c * 32 + lane;
@@ -172,12 +186,10 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
           float s = 0.f, dp = 0.f;
           const T* qr = sQ + i * LDS;
           const T* dor = sdO + i * LDS;
-          const T* kr = sK + j * LDS;
-          const T* vr = sV + j * LDS;
 #pragma unroll 16
           for (int d = 0; d < DH; ++d) {
-            s = fmaf(to_f<T>(qr[d]), to_f<T>(kr[d]), s);
-            dp = fmaf(to_f<T>(dor[d]), to_f<T>(vr[d]), dp);
+            s = fmaf(to_f<T>(qr[d]), rowA[d], s);
+            dp = fmaf(to_f<T>(dor[d]), rowB[d], dp);
           }
           p = __expf(s * a.scale - sLse[i]);
           ds = p * (dp - sDelta[i]);
@@ -202,9 +214,20 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
     gdv[lane] = from_f<T>(v0);
     gdv[lane + 32] = from_f<T>(v1);
   }
-  // ---- phase B: each warp owns queries i = w, w+4, ...
+  // ---- phase B: the tiles now hold K and V; each warp owns queries i = w, w+4, ...
+  __syncthreads();
+  T* sK = sT0;
+  T* sV = sT1;
+  load_head<T>(sK, gk, a.ld, S, LDS);
+  load_head<T>(sV, gv, a.ld, S, LDS);
+  __syncthreads();
   float* rowDS = sBufA + w * S;
   for (int i = w; i < S; i += 4) {
+    __syncwarp();
+    rowA[lane] = to_f<T>(gq[(long long)i * a.ld + lane]);
+    rowA[lane + 32] = to_f<T>(gq[(long long)i * a.ld + lane + 32]);
+    rowB[lane] = to_f<T>(gdo[(long long)i * a.ldo + lane]);
+    rowB[lane + 32] = to_f<T>(gdo[(long long)i * a.ldo + lane + 32]);
     __syncwarp();
     for (int c = 0; c < nch; ++c) {
       const int j = c * 32 + lane;
@@ -212,14 +235,12 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
         float ds = 0.f;
         if (allowed(a, sTraj, nullptr, i, j)) {
           float s = 0.f, dp = 0.f;
-          const T* qr = sQ + i * LDS;
-          const T* dor = sdO + i * LDS;
           const T* kr = sK + j * LDS;
           const T* vr = sV + j * LDS;
 #pragma unroll 16
           for (int d = 0; d < DH; ++d) {
-            s = fmaf(to_f<T>(qr[d]), to_f<T>(kr[d]), s);
-            dp = fmaf(to_f<T>(dor[d]), to_f<T>(vr[d]), dp);
+            s = fmaf(rowA[d], to_f<T>(kr[d]), s);
+            dp = fmaf(rowB[d], to_f<T>(vr[d]), dp);
           }
           ds = __expf(s * a.scale - sLse[i]) * (dp - sDelta[i]);
         }
@@ -246,8 +267,8 @@ template <typename T> size_t fwd_smem(int S) {
 }
 template <typename T> size_t bwd_smem(int S) {
   constexpr int LDS = DH + Pad<T>::v;
-  size_t e = (size_t)4 * S * LDS;
-  return e * sizeof(T) + sizeof(float) * (2 * S + 8 * S) + sizeof(int) * S + 16;
+  size_t e = (size_t)2 * S * LDS;
+  return e * sizeof(T) + sizeof(float) * (2 * S + 8 * S + 8 * DH) + sizeof(int) * S + 16;
 }
 
 }  // namespace

@@ -105,8 +105,6 @@ class _LogGradBase(PPO):
 
     def __init__(self, discrete_critics: bool, action_loss_schedule: Optional[Callable], *args, **kwargs):
         super().__init__(*args, **kwargs)
-        if discrete_critics:
-            raise NotImplementedError("critic_type='discrete' (HLGauss head) is not on the shipped path")
         self.discrete_critics = discrete_critics
         self.action_loss_schedule = action_loss_schedule if action_loss_schedule is not None else (lambda x: 1.0)
         self.c_adv_key = "c_" + self.adv_key
@@ -121,9 +119,21 @@ class _LogGradBase(PPO):
                           self.entropy_coef, 0.0, 1.0 / n, 1.0, int(self.use_clipped_value_loss),
                           int(self._lagrangian))
         lm = kwargs["lagrangian_multiplier"] if self._lagrangian else None
+        dc_value = None
+        if self.discrete_critics:
+            # customized_loss.py:364-370: value_loss = 0.5 * HLGauss(extras["full_logits"], returns); the fused kernel
+            # evaluates the action / entropy terms, the HL-Gauss kernel the value term (loss + d / d logits in one pass)
+            ex = actor_critic_output.extras
+            fl = ex["full_logits"]
+            dc_value = 0.5 * ex["loss_func"](fl.reshape(-1, fl.shape[-1]), batch["returns"].to(fl.device).reshape(-1))
+            values = None
         total, scal = fused_ppo_loss(logits=logits, values=values, c_values=None, batch=batch, hp=hp,
                                      lagrangian_multiplier=lm, adv_key=self.adv_key, c_adv_key=self.c_adv_key)
         s = scal.tolist()  # the one host sync of this loss
+        if dc_value is not None:
+            total = total + self.value_loss_coef * dc_value
+            s[1] = float(dc_value)
+            s[0] = float(total)
         if s[10] != 0.0:
             raise ValueError(f"{int(s[10])} action indices outside [0, {logits.shape[-1]}): batch['actions'] is corrupted "
                              "or mis-shaped")

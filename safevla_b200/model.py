@@ -83,6 +83,25 @@ class _TowerOutput(torch.autograd.Function):
         return None, None, None, None, None
 
 
+class _TowerOutputPair(torch.autograd.Function):
+    """Discrete-critic towers return (values, bin logits); the losses differentiate the logits
+    (customized_loss.py:364-370), the value read-out carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, idx, state, values, full_logits):
+        ctx.model, ctx.idx, ctx.state = model, idx, state
+        ctx.set_materialize_grads(False)
+        return values.view_as(values), full_logits.view_as(full_logits)
+
+    @staticmethod
+    def backward(ctx, g_values, g_logits):
+        if g_values is not None:
+            raise NotImplementedError("discrete critic: only the bin logits are differentiated")
+        if g_logits is not None:
+            ctx.model._tower_backward_autograd(ctx.idx, ctx.state, None, dfull=g_logits.contiguous())
+        return None, None, None, None, None, None
+
+
 class B200SafeActorCritic(nn.Module):
     def __init__(self, num_actions: int, num_cameras: int = 1, *, precision: str = "bf16",
                  device: Optional[torch.device] = None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
@@ -91,7 +110,8 @@ class B200SafeActorCritic(nn.Module):
                  goal_sensor_uuid: str = "natural_language_spec", rgb_uuid: str = "rgb_dinov2",
                  manip_uuid: str = "manipulation_rgb_dinov2", in_hand_uuid: str = "an_object_is_in_hand",
                  time_step_uuid: str = "time_step", traj_idx_uuid: str = "traj_index", extras: str = "eager",
-                 verify_dedupe: bool = True, max_steps: int = 1000, num_cost_channels: int = 1):
+                 verify_dedupe: bool = True, max_steps: int = 1000, num_cost_channels: int = 1,
+                 critic_type: str = "linear"):
         super().__init__()
         # "bf16": bf16 operands on the tcgen05 kernels (the fast path); "fp32": fp32 FMA kernels (CUDA cores);
         # "bf16x3" / "bf16x6": fp32 activations and weights, every tensor-core-shaped product evaluated on the tcgen05
@@ -114,7 +134,14 @@ class B200SafeActorCritic(nn.Module):
         self.extras_mode, self.verify_dedupe = extras, verify_dedupe
         self.trainable_towers: Tuple[int, ...] = (ACTOR, CRITIC, COST)
 
-        self.layout, self.t5_layout = ParamLayout(num_actions, num_cameras, self.K), T5Layout()
+        # "linear" (shipped, allenact_dino_transformer.py:148-149) or "discrete" (HL-Gauss DiscreteCriticHead, :152-159)
+        self.critic_type = critic_type
+        self.dc_loss = None
+        if critic_type == "discrete":
+            from .losses import HLGaussLoss
+            from .params import DC_BINS, DC_MAX, DC_MIN, DC_SIGMA
+            self.dc_loss = HLGaussLoss(min_value=DC_MIN, max_value=DC_MAX, num_bins=DC_BINS, sigma=DC_SIGMA)
+        self.layout, self.t5_layout = ParamLayout(num_actions, num_cameras, self.K, critic_type), T5Layout()
         f32 = dict(device=self.dev, dtype=torch.float32)
         self.param_arena = torch.zeros(self.layout.total, **f32)
         self.grad_arena = torch.zeros(self.layout.total, **f32)
@@ -123,7 +150,8 @@ class B200SafeActorCritic(nn.Module):
         self.t5_arena = torch.zeros(self.t5_layout.total, **f32)
         self._register_names()
         self.load_state_dict(state_dict if state_dict is not None
-                             else init_state_dict(num_actions, num_cameras, seed, num_cost_channels=self.K), strict=True)
+                             else init_state_dict(num_actions, num_cameras, seed, num_cost_channels=self.K,
+                                                  critic_type=critic_type), strict=True)
 
         self.t5 = T5Encoder(self.t5_layout, self.t5_arena, self.adt, self.split)
         if self.split:
@@ -155,7 +183,7 @@ class B200SafeActorCritic(nn.Module):
 
     def _register_names(self):
         for ti, pre in enumerate(TOWERS):
-            for k, shape, _ in tower_spec(self.A, self.C, tower_values(ti, self.K)):
+            for k, shape, _ in tower_spec(self.A, self.C, tower_values(ti, self.K), self.critic_type):
                 name = pre + k
                 parts = name.split(".")
                 p = nn.Parameter(self.layout.view(self.param_arena, name), requires_grad=True)
@@ -323,10 +351,10 @@ class B200SafeActorCritic(nn.Module):
                      stash_all=stash_all) if keep else None
         return out, state
 
-    def tower_backward(self, idx: int, state, dlogits, dvalues):
+    def tower_backward(self, idx: int, state, dlogits, dvalues, dfull=None):
         tw, rc = self.towers[idx], state["rc"]
         d_obs = tw.decoder_bwd(dlogits, dvalues, state["dec"], state["prev"], state["masks"], rc.in_hand,
-                               rc.traj_nt, rc.perm_nt, rc.T, rc.N)
+                               rc.traj_nt, rc.perm_nt, rc.T, rc.N, dfull=dfull)
         state["dec"] = None
         for ci, (r0, r1) in enumerate(state["chunks"]):
             vis, th = self._chunk_inputs(rc, r0, r1)
@@ -336,13 +364,14 @@ class B200SafeActorCritic(nn.Module):
             tw.encoder_bwd(d_obs[r0:r1], vis, th, rc.L, st)
             state["enc"][ci] = None
 
-    def _tower_backward_autograd(self, idx: int, state, grad_out: torch.Tensor):
+    def _tower_backward_autograd(self, idx: int, state, grad_out: Optional[torch.Tensor], dfull=None):
         pre = TOWERS[idx]
         sentinel = self.get_parameter(pre + "decoder.norm.weight")
         if sentinel.grad is None:  # optimizer.zero_grad(set_to_none=True) happened: arena slice is stale
             lo, hi = self.layout.tower_range[pre]
             self.grad_arena[lo:hi].zero_()
-        self.tower_backward(idx, state, grad_out if idx == ACTOR else None, grad_out if idx != ACTOR else None)
+        self.tower_backward(idx, state, grad_out if idx == ACTOR else None, grad_out if idx != ACTOR else None,
+                            dfull=dfull)
         self.attach_grads()
 
     # ------------------------------------------------------------------ nn.Module forward (drop-in)
@@ -362,10 +391,15 @@ class B200SafeActorCritic(nn.Module):
             o, state = self.tower_forward(idx, rc, pa, mk, keep=keep, want_logits=(idx == ACTOR),
                                           want_values=(idx != ACTOR))
             t = o["logits"] if idx == ACTOR else o["values"]
-            if keep:
+            fl = o.get("full_logits")
+            if keep and fl is not None:
+                t, fl = _TowerOutputPair.apply(self._anchor, self, idx, state, t, fl)
+            elif keep:
                 t = _TowerOutput.apply(self._anchor, self, idx, state, t)
             outs[idx] = t
-        extras = self._extras(outs[COST])
+            if idx == COST:
+                cost_logits = fl
+        extras = self._extras(outs[COST], cost_logits)
         aco = SafeActorCriticOutput(distributions=CategoricalDistr(logits=outs[ACTOR]), values=outs[CRITIC],
                                     c_values=outs[COST], extras=extras)
         return aco, memory
@@ -394,24 +428,38 @@ class B200SafeActorCritic(nn.Module):
             o = tw.decoder_step(obs_embed, pa, mk, rc.in_hand, rc.time_step, kv[idx], pos, N,
                                 want_logits=(idx == ACTOR), want_values=(idx != ACTOR))
             outs[idx] = o["logits"] if idx == ACTOR else o["values"]
+            if idx == COST:
+                cost_logits = o.get("full_logits")
         self.time_step_counter += 1
         aco = SafeActorCriticOutput(distributions=CategoricalDistr(logits=outs[ACTOR]), values=outs[CRITIC],
-                                    c_values=outs[COST], extras=self._extras(outs[COST]))
+                                    c_values=outs[COST], extras=self._extras(outs[COST], cost_logits))
         return aco, memory
 
-    def _extras(self, c_values: torch.Tensor):
+    def _extras(self, c_values: torch.Tensor, cost_logits: Optional[torch.Tensor] = None):
         """Logging extras with the reference's quirks: they describe the COST tower
-        (separate_actor_critic.py:35) and are 1-element CPU tensors (allenact_dino_transformer.py:431-455)."""
+        (separate_actor_critic.py:35) and are 1-element CPU tensors (allenact_dino_transformer.py:431-455).
+        Discrete critics (:434-439): `full_logits` / `stop_grad_logits` / `loss_func` are the COST tower's too -- which
+        is what SafePPOLogGrad's value term then trains (customized_loss.py:364-370), a quirk kept as it is."""
+        disc = {}
+        if self.critic_type == "discrete" and cost_logits is not None:
+            disc = {"full_logits": cost_logits, "stop_grad_logits": cost_logits.detach(), "loss_func": self.dc_loss}
         if self.extras_mode == "off":
-            return {}
+            return disc
         pre = TOWERS[COST]
         lo, hi = self.layout.tower_range[pre]
         buf = torch.empty(4, device=self.dev)
         ops.sq_norm(self.grad_arena[lo:hi], buf[0:1])
-        wslot, bslot = self.layout.slots[pre + "critic.fc.weight"], self.layout.slots[pre + "critic.fc.bias"]
+        head = "critic.fc.2." if self.critic_type == "discrete" else "critic.fc."  # fc[-1] of the MLP heads (:456-468)
+        wslot, bslot = self.layout.slots[pre + head + "weight"], self.layout.slots[pre + head + "bias"]
         ops.sq_norm(self.param_arena[wslot.offset: wslot.offset + wslot.numel], buf[1:2])
-        ops.sq_norm(self.param_arena[bslot.offset: bslot.offset + 4], buf[2:3])  # padded slot: zeros beyond [1]
+        nb = (bslot.numel + 3) // 4 * 4  # slots are padded with zeros to 64 elements
+        ops.sq_norm(self.param_arena[bslot.offset: bslot.offset + nb], buf[2:3])
         ops.sq_norm(self.grad_arena[wslot.offset: wslot.offset + wslot.numel], buf[3:4])
         host = buf.cpu().sqrt()
-        return {"total_norm": host[0:1].clone(), "weight_norm": host[1:2].clone(), "bias_norm": host[2:3].clone(),
-                "weight_grad_norm": host[3:4].clone(), "stop_grad_values": c_values.detach()}
+        ex = {"total_norm": host[0:1].clone(), "weight_norm": host[1:2].clone(), "bias_norm": host[2:3].clone(),
+              "weight_grad_norm": host[3:4].clone()}
+        if disc:
+            ex.update(disc)
+        else:
+            ex["stop_grad_values"] = c_values.detach()
+        return ex

@@ -24,9 +24,15 @@ T5_VOCAB = 32128
 ALIGN = 64  # elements; keeps every tensor 256 B (fp32) / 128 B (bf16) aligned for TMA
 
 
-def tower_spec(num_actions: int, num_cameras: int, num_values: int = 1) -> List[Tuple[str, Tuple[int, ...], str]]:
+DC_HIDDEN, DC_BINS = 256, 101  # DiscreteCriticHead: 512 -> 256 -> 101 bins (allenact_dino_transformer.py:152-159,743-766)
+DC_MIN, DC_MAX, DC_SIGMA = -5.0, 15.0, 0.15
+
+
+def tower_spec(num_actions: int, num_cameras: int, num_values: int = 1,
+               critic_type: str = "linear") -> List[Tuple[str, Tuple[int, ...], str]]:
     """(name, shape, init) for the trainable tensors of ONE tower, in reference state_dict order.  `num_values` is the
-    width of the critic head: 1 in the reference; K for the cost tower of the K-cost-channel extension."""
+    width of the critic head: 1 in the reference; K for the cost tower of the K-cost-channel extension.
+    critic_type "linear" (shipped) or "discrete" (HL-Gauss DiscreteCriticHead: critic.fc.0 / critic.fc.2)."""
     ve = "visual_encoder."
     s: List[Tuple[str, Tuple[int, ...], str]] = [
         (ve + "fusion_token", (D,), "token"),
@@ -85,9 +91,15 @@ def tower_spec(num_actions: int, num_cameras: int, num_values: int = 1) -> List[
         ("decoder.output.weight", (D, D), "linear"),
         ("actor.linear.weight", (num_actions, D), "actor"),
         ("actor.linear.bias", (num_actions,), "zeros"),
-        ("critic.fc.weight", (num_values, D), "critic"),
-        ("critic.fc.bias", (num_values,), "zeros"),
     ]
+    if critic_type == "discrete":
+        assert num_values == 1, "the discrete critic head predicts one value"
+        s += [("critic.fc.0.weight", (DC_HIDDEN, D), "critic"), ("critic.fc.0.bias", (DC_HIDDEN,), "zeros"),
+              ("critic.fc.2.weight", (DC_BINS, DC_HIDDEN), "critic"), ("critic.fc.2.bias", (DC_BINS,), "zeros")]
+    elif critic_type == "linear":
+        s += [("critic.fc.weight", (num_values, D), "critic"), ("critic.fc.bias", (num_values,), "zeros")]
+    else:
+        raise NotImplementedError(f"critic_type={critic_type!r}: 'linear' and 'discrete' are built")
     return s
 
 
@@ -148,7 +160,7 @@ def tower_values(tower_index: int, num_cost_channels: int) -> int:
 
 
 def init_state_dict(num_actions: int, num_cameras: int, seed: int, actor_gain: float = 0.01,
-                    num_cost_channels: int = 1) -> "OrderedDict[str, torch.Tensor]":
+                    num_cost_channels: int = 1, critic_type: str = "linear") -> "OrderedDict[str, torch.Tensor]":
     """Deterministic (CPU generator) random init with the reference's key set; the three towers
     get independent trainable weights and the SAME frozen T5 weights (as `from_pretrained` gives)."""
     g = torch.Generator().manual_seed(seed)
@@ -156,7 +168,7 @@ def init_state_dict(num_actions: int, num_cameras: int, seed: int, actor_gain: f
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     div_term = torch.exp(torch.arange(0, D, 2) * (-math.log(10000.0) / D))
     for ti, pre in enumerate(TOWERS):
-        for k, shape, kind in tower_spec(num_actions, num_cameras, tower_values(ti, num_cost_channels)):
+        for k, shape, kind in tower_spec(num_actions, num_cameras, tower_values(ti, num_cost_channels), critic_type):
             sd[pre + k] = _init(shape, kind, g, actor_gain)
             if k == "last_actions_embed.weight":
                 sd[pre + k][num_actions + 1].zero_()  # padding_idx row
@@ -180,14 +192,15 @@ class Slot:
 class ParamLayout:
     """Offsets of every trainable tensor inside the flat arena (all three towers)."""
 
-    def __init__(self, num_actions: int, num_cameras: int, num_cost_channels: int = 1):
+    def __init__(self, num_actions: int, num_cameras: int, num_cost_channels: int = 1, critic_type: str = "linear"):
         self.num_actions, self.num_cameras, self.num_cost_channels = num_actions, num_cameras, num_cost_channels
+        self.critic_type = critic_type
         self.slots: "OrderedDict[str, Slot]" = OrderedDict()
         self.tower_range: Dict[str, Tuple[int, int]] = {}
         off = 0
         for ti, pre in enumerate(TOWERS):
             start = off
-            for k, shape, _ in tower_spec(num_actions, num_cameras, tower_values(ti, num_cost_channels)):
+            for k, shape, _ in tower_spec(num_actions, num_cameras, tower_values(ti, num_cost_channels), critic_type):
                 n = int(torch.Size(shape).numel())
                 self.slots[pre + k] = Slot(pre + k, shape, off, n)
                 off += (n + ALIGN - 1) // ALIGN * ALIGN

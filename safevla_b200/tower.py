@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 from ._lib import ATTN_FULL, ATTN_T5_BIAS, ATTN_TRAJ_CAUSAL, EPI_NONE, EPI_RELU, EPI_RELU_MASK, RowMap
-from .params import D, DEC_FF, FF, ParamLayout, T5Layout
+from .params import D, DC_BINS, DC_HIDDEN, DC_MAX, DC_MIN, DC_SIGMA, DEC_FF, FF, ParamLayout, T5Layout
 
 H, DH = 8, 64
 LN_EPS, RMS_EPS, T5_EPS = 1e-5, 1e-5, 1e-6
@@ -72,6 +72,9 @@ class Tower:
         self.adt = act_dtype  # encoder activation dtype
         self.cls_only = cls_only_last_layer
         self.dev = weights.params.device
+        self.critic_type = weights.layout.critic_type
+        self.dc_support = (torch.linspace(DC_MIN, DC_MAX, DC_BINS + 1, device=self.dev, dtype=torch.float32)
+                           if self.critic_type == "discrete" else None)
         # parity-grade tensor-core mode: fp32 activations / weights, every tensor-core-shaped product evaluated as
         # 3 (or 6) split-bf16 products in one tcgen05 launch (ops.gemm split=); 0 = operands as they are
         self.split = split
@@ -292,8 +295,6 @@ class Tower:
         ops.embed_time_fwd(obs_embed, prev_actions, masks, in_hand, time_step, W.p("last_actions_embed.weight"),
                            W.p("object_in_hand_embed.weight") if in_hand is not None else None,
                            self.div_term, x, T, N, self.A)
-        if ddt == f32 and T > 208:
-            raise NotImplementedError("fp32 parity mode supports T <= 208 (shared-memory attention tile)")
         h = x
         for l in range(3):
             p = f"decoder.layers.{l}."
@@ -322,7 +323,18 @@ class Tower:
         if want_logits:
             out["logits"] = self._gemm(b_tn, W.p("actor.linear.weight"), self._new(Md, self.A, dtype=f32),
                                      bias=W.p("actor.linear.bias")).view(T, N, self.A)
-        if want_values:
+        if want_values and self.critic_type == "discrete":
+            # DiscreteCriticHead (allenact_dino_transformer.py:743-766): 512 -> 256 -> ReLU -> 101 bin logits, value =
+            # HL-Gauss read-out of softmax(logits) (one fused launch)
+            h1 = self._gemm(b_tn, W.p("critic.fc.0.weight"), self._new(Md, DC_HIDDEN, dtype=f32),
+                            bias=W.p("critic.fc.0.bias"), epilogue=EPI_RELU)
+            fl = self._gemm(h1, W.p("critic.fc.2.weight"), self._new(Md, DC_BINS, dtype=f32), bias=W.p("critic.fc.2.bias"))
+            _, _, vals = ops.hl_gauss_fwd_bwd(fl, torch.zeros(Md, device=self.dev), self.dc_support, DC_SIGMA,
+                                              want_grad=False, want_values=True)
+            out["values"], out["full_logits"] = vals.view(T, N, 1), fl.view(T, N, DC_BINS)
+            if keep:
+                t.update({"dc_h1": h1})
+        elif want_values:
             nv = W.p("critic.fc.weight").shape[0]  # 1, or K for the cost tower of the K-cost-channel extension
             out["values"] = self._gemm(b_tn, W.p("critic.fc.weight"), self._new(Md, nv, dtype=f32),
                                      bias=W.p("critic.fc.bias")).view(T, N, nv)
@@ -364,14 +376,22 @@ class Tower:
         if want_logits:
             out["logits"] = self._gemm(b, W.p("actor.linear.weight"), self._new(N, self.A, dtype=f32),
                                      bias=W.p("actor.linear.bias")).view(1, N, self.A)
-        if want_values:
+        if want_values and self.critic_type == "discrete":
+            h1 = self._gemm(b, W.p("critic.fc.0.weight"), self._new(N, DC_HIDDEN, dtype=f32), bias=W.p("critic.fc.0.bias"),
+                            epilogue=EPI_RELU)
+            fl = self._gemm(h1, W.p("critic.fc.2.weight"), self._new(N, DC_BINS, dtype=f32), bias=W.p("critic.fc.2.bias"))
+            _, _, vals = ops.hl_gauss_fwd_bwd(fl, torch.zeros(N, device=self.dev), self.dc_support, DC_SIGMA,
+                                              want_grad=False, want_values=True)
+            out["values"], out["full_logits"] = vals.view(1, N, 1), fl.view(1, N, DC_BINS)
+        elif want_values:
             nv = W.p("critic.fc.weight").shape[0]
             out["values"] = self._gemm(b, W.p("critic.fc.weight"), self._new(N, nv, dtype=f32),
                                      bias=W.p("critic.fc.bias")).view(1, N, nv)
         return out
 
-    def decoder_bwd(self, dlogits, dvalues, t, prev_actions, masks, in_hand, traj_nt, perm_nt, T, N):
-        """Returns d obs_embed [T*N, 512] (adt).  perm_nt[n*T+t] = t*N+n."""
+    def decoder_bwd(self, dlogits, dvalues, t, prev_actions, masks, in_hand, traj_nt, perm_nt, T, N, dfull=None):
+        """Returns d obs_embed [T*N, 512] (adt).  perm_nt[n*T+t] = t*N+n.  dfull: gradient of the discrete critic's
+        bin logits [T, N, 101] (the HL-Gauss loss differentiates those, customized_loss.py:364-370)."""
         W, f32, ddt = self.W, torch.float32, self.adt
         Md = T * N
 
@@ -384,7 +404,22 @@ class Tower:
             self._gemm(dl, t["b_tn"], W.g("actor.linear.weight"), trans_a=True, trans_b=False, accumulate=True)
             ops.colsum(dl, W.g("actor.linear.bias"), accumulate=True)
             db_tn = self._gemm(dl, W.p("actor.linear.weight"), self._new(Md, D, dtype=f32), trans_b=False)
-        if dvalues is not None:
+        if self.critic_type == "discrete":
+            if dvalues is not None:
+                raise NotImplementedError("discrete critic: gradients flow through the bin logits (extras['full_logits']), "
+                                          "as in the reference's losses; the value read-out is not differentiated")
+            if dfull is not None:
+                dfl = dfull.reshape(Md, DC_BINS).contiguous()
+                h1 = t["dc_h1"]
+                self._gemm(dfl, h1, W.g("critic.fc.2.weight"), trans_a=True, trans_b=False, accumulate=True)
+                ops.colsum(dfl, W.g("critic.fc.2.bias"), accumulate=True)
+                dh1 = self._gemm(dfl, W.p("critic.fc.2.weight"), self._new(Md, DC_HIDDEN, dtype=f32), trans_b=False, aux=h1,
+                                 epilogue=EPI_RELU_MASK)
+                self._gemm(dh1, t["b_tn"], W.g("critic.fc.0.weight"), trans_a=True, trans_b=False, accumulate=True)
+                ops.colsum(dh1, W.g("critic.fc.0.bias"), accumulate=True)
+                db_tn = self._gemm(dh1, W.p("critic.fc.0.weight"), self._new(Md, D, dtype=f32), trans_b=False,
+                                   residual=db_tn)
+        elif dvalues is not None:
             dv = dvalues.view(Md, -1)
             self._gemm(dv, t["b_tn"], W.g("critic.fc.weight"), trans_a=True, trans_b=False, accumulate=True)
             ops.colsum(dv, W.g("critic.fc.bias"), accumulate=True)

@@ -61,6 +61,47 @@ def test_oracle_reproduces_reference_golden(name):
     assert abs(t0.item() - gold["loss_lambda0"].item()) < 1e-5 * max(1, abs(t0.item()))
 
 
+def test_oracle_reproduces_discrete_critic_golden():
+    """critic_type="discrete" (DiscreteCriticHead + HL-Gauss, allenact_dino_transformer.py:152-159,434-439,743-766)
+    with SafePPOLogGrad(discrete_critics=True) (customized_loss.py:364-370): the restated oracle against the reference's
+    own outputs -- incl. the quirk that the value term trains the COST tower's head on the reward returns."""
+    from oracle.make_golden import DISCRETE_CASES
+    torch.set_num_threads(os.cpu_count() or 1)
+    (name, case), = DISCRETE_CASES.items()
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    T, N, A, C = case["T"], case["N"], case["A"], case["C"]
+    sd = init_state_dict(A, C, case["wseed"], actor_gain=1.0, critic_type="discrete")
+    assert sd["c_critic_tsfm.critic.fc.0.weight"].shape == (256, 512) and sd["critic.fc.2.weight"].shape == (101, 256)
+    spec, ro, extra = build_inputs(case)
+    obs = {k: v[:-1] for k, v in ro["observations"].items()}
+    prev, masks = prev_actions_from(ro["actions"]), ro["masks"][:-1]
+    leaf = {k: (v.clone().requires_grad_(True) if "text_encoder" not in k and not k.endswith("div_term") else v)
+            for k, v in sd.items()}
+    out = TO.safe_model_forward(leaf, obs, prev, masks, A, C)
+    for k in ("logits", "values", "c_values", "full_logits"):
+        assert relerr(out[k], gold[k]) < 2e-5, k
+    ret, adv = TO.gae_returns(ro["rewards"], extra["value_preds"], ro["masks"], 0.99, 0.95)
+    _, cadv = TO.gae_returns(ro["costs"], extra["c_value_preds"], ro["masks"], 0.99, 0.95)
+    # action + entropy terms as usual (value weight 0), value term = 0.5 * HLGauss(cost-tower logits, reward returns)
+    pol, info = TO.safe_ppo_log_grad(out["logits"], ro["actions"], gold["old_logp"], adv, cadv, out["values"].detach(),
+                                     ret[:-1], case["lam"], entropy_coef=0.01, value_loss_coef=0.0)
+    vl = 0.5 * TO.hl_gauss_loss(out["full_logits"].reshape(T * N, -1), ret[:-1].reshape(-1),
+                                TO.hl_gauss_support(-5.0, 15.0, 101), 0.15)
+    total = pol + 0.5 * vl
+    assert abs(vl.item() - gold["info"]["value"]) < 1e-5 * max(1, abs(gold["info"]["value"]))
+    assert abs(total.item() - gold["loss_total"].item()) < 1e-5 * max(1, abs(gold["loss_total"].item()))
+    total.backward()
+    for k, gn in gold["grad_norms"].items():
+        g = leaf[k].grad
+        if gn is None:
+            assert g is None or g.abs().max() == 0, k
+        else:
+            assert abs(g.norm().item() - gn) / max(gn, 1e-8) < 1e-3, k
+    # the reward critic tower receives NO gradient, the cost tower does
+    assert gold["grad_norms"]["critic_tsfm.decoder.norm.weight"] is None
+    assert gold["grad_norms"]["c_critic_tsfm.critic.fc.2.weight"] > 0
+
+
 @pytest.mark.parametrize("name", ["step_N3_A6_C1", "step_N2_A20_C2"])
 def test_oracle_step_mode_reproduces_reference_golden(name):
     """Rollout-side T = 1 path (KV-cache decoder, episode-start mask, position wrap at max_steps, reset by an
@@ -292,6 +333,57 @@ def test_checkpoint_format_conversion():
     assert not any("critic_tsfm" in k for k in CK.strip_critic_towers(sd))
     with pytest.raises(ValueError):
         CK.detect_format({"weights": 1})
+
+
+def test_il_checkpoint_merge_equals_reference_loader(tmp_path):
+    """f-3: `checkpoint.merge_il_checkpoint` against the reference's OWN `load_pl_ckpt_allenact`
+    (training/offline/train_utils.py:6-68) executed through the shim on a synthetic PyTorch-Lightning file: IL head
+    names (`actor.weight`), the `model.` prefix, frozen DINO weights to be ignored, keys missing from the checkpoint
+    (an IL policy has no critic head) and an unexpected key.  Every tower's constructor receives `prev_checkpoint`
+    (allenact_dino_transformer.py:169-176, separate_actor_critic.py:8-11,23-25), so the reference loader is applied to
+    each of the three tower modules."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present on this box")
+    import contextlib
+    import io
+    from safevla_b200 import checkpoint as CK
+    ref_shim.reference_modules()
+    from training.offline.train_utils import load_pl_ckpt_allenact
+    A, C = 6, 1
+    sd0 = init_state_dict(A, C, 41, actor_gain=1.0)
+    il = init_state_dict(A, C, 42, actor_gain=1.0)  # a different single-tower policy plays the IL model
+    ckpt_sd = {}
+    for k, shape, _ in tower_spec(A, C):
+        if k.startswith("critic.") or k == "decoder.layers.1.ffn_norm.weight":
+            continue  # absent from the IL checkpoint: the model keeps its own value
+        name = {"actor.linear.weight": "actor.weight", "actor.linear.bias": "actor.bias"}.get(k, k)
+        ckpt_sd["model." + name] = il[k].clone()
+    ckpt_sd["model.visual_encoder.image_encoder.model.blocks.0.attn.qkv.weight"] = torch.randn(8, 8)  # frozen DINO
+    ckpt_sd["model.some_il_only_head.weight"] = torch.randn(3, 3)  # unexpected
+    for k, v in il.items():
+        if k.startswith("visual_encoder.text_encoder."):
+            ckpt_sd["model." + k] = v.clone() + 0.5  # the IL file carries its own T5 copy
+    ckpt = {"state_dict": ckpt_sd, "epoch": 3}
+    path = str(tmp_path / "il.ckpt")
+    torch.save(ckpt, path)
+    # ---- the reference loader, tower by tower
+    model = ref_shim.build_reference_model(A, C, seed=0)
+    model.load_state_dict(sd0, strict=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for tower in (model, model.critic_tsfm, model.c_critic_tsfm):
+            load_pl_ckpt_allenact(tower, path, ckpt_prefix="model.")
+    ref_state = model.state_dict()
+    # ---- ours
+    new, report = CK.merge_il_checkpoint(sd0, torch.load(path, weights_only=False))
+    assert set(new) == set(ref_state)
+    for k, v in ref_state.items():
+        assert torch.equal(new[k], v), k
+    assert "actor.linear.weight" in report.loaded and "decoder.layers.1.ffn_norm.weight" in report.missing_in_checkpoint
+    assert "critic.fc.weight" in report.missing_in_checkpoint
+    assert report.unexpected_in_checkpoint == ["some_il_only_head.weight"]
+    assert torch.equal(new["critic_tsfm.visual_encoder.text_adapter.0.weight"], il["visual_encoder.text_adapter.0.weight"])
+    assert torch.equal(new["c_critic_tsfm.critic.fc.weight"], sd0["c_critic_tsfm.critic.fc.weight"])
 
 
 def test_hl_gauss_oracle_reproduces_reference_golden():

@@ -99,6 +99,47 @@ def test_golden_stage0_value_losses(dev):
             assert abs(p.grad.norm().item() - gn) / max(gn, 1e-8) < 2e-3, k
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_discrete_critic_matches_reference_golden(dev, precision):
+    """critic_type="discrete" end to end: DiscreteCriticHead in every tower, extras["full_logits" | "loss_func" |
+    "stop_grad_logits"] (allenact_dino_transformer.py:434-439), SafePPOLogGrad(discrete_critics=True)
+    (customized_loss.py:364-370) -- forward, loss terms and every parameter-gradient norm against the reference."""
+    from oracle.make_golden import DISCRETE_CASES
+    from safevla_b200.losses import HLGaussLoss, SafePPOLogGrad
+    from safevla_b200.model import B200SafeActorCritic
+    (name, case), = DISCRETE_CASES.items()
+    gold = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    sd = init_state_dict(case["A"], case["C"], case["wseed"], actor_gain=1.0, critic_type="discrete")
+    model = B200SafeActorCritic(case["A"], case["C"], precision=precision, state_dict=sd, device=dev, critic_type="discrete")
+    assert set(model.state_dict()) == set(sd)
+    spec, ro, extra = build_inputs(case)
+    obs = {k: v[:-1].to(dev) for k, v in ro["observations"].items()}
+    out, _ = model(obs, None, prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev))
+    tol = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 4e-2}[precision]
+    ex = out.extras
+    assert isinstance(ex["loss_func"], HLGaussLoss) and torch.equal(ex["stop_grad_logits"], ex["full_logits"].detach())
+    for got, key in ((out.distributions.raw_logits, "logits"), (out.values, "values"), (out.c_values, "c_values"),
+                     (ex["full_logits"], "full_logits")):
+        assert got.shape == gold[key].shape and relerr(got, gold[key]) < tol, (key, relerr(got, gold[key]))
+    loss = SafePPOLogGrad(clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.01, use_clipped_value_loss=False,
+                          action_loss_schedule=None, discrete_critics=True, normalize_advantage=False)
+    total, info = loss.loss(0, _batch(gold, ro, extra, dev), out, lagrangian_multiplier=torch.tensor(case["lam"]))
+    ltol = 1e-4 if precision != "bf16" else 5e-3
+    for k in ("ppo_total", "value", "action", "entropy"):
+        assert abs(info[k] - gold["info"][k]) <= ltol * max(1.0, abs(gold["info"][k])), (k, info[k], gold["info"][k])
+    total.backward()
+    gtol = 2e-3 if precision != "bf16" else 5e-2
+    for k, gn in gold["grad_norms"].items():
+        p = model.get_parameter(k)
+        if gn is None:  # incl. the whole reward-critic tower: the value term trains the COST tower's head
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+        else:
+            assert abs(p.grad.norm().item() - gn) / max(gn, 1e-8) < gtol, (k, p.grad.norm().item(), gn)
+    if precision == "fp32":
+        for k, gref in gold["grads"].items():
+            assert relerr(model.get_parameter(k).grad, gref) < 2e-3, k
+
+
 def test_golden_bf16_mode(dev):
     """bf16 tensor-core mode: same path, looser tolerance (bf16 operands, fp32 accumulation)."""
     gold, case, model, ro, extra, obs = _setup("cfg1_T16_N1_A6_C1", dev, "bf16")
