@@ -162,7 +162,14 @@ typedef enum {
   SVLA_EPI_NONE = 0,
   SVLA_EPI_RELU = 1,        /* C = relu(acc + bias) */
   SVLA_EPI_RELU_MASK = 2,   /* C = (acc + bias) * (aux > 0): ReLU backward fused into a dgrad */
-  SVLA_EPI_GELU = 3         /* C = gelu_erf(acc + bias): DINOv2 MLP (vision preprocessor, forward only) */
+  SVLA_EPI_GELU = 3,        /* C = gelu_erf(acc + bias): DINOv2 MLP (vision preprocessor, forward only) */
+  /* ReLU with a one-bit-per-element record instead of re-reading the activation in the backward: the K = 512 GEMMs
+   * of the fusion block are HBM-bound, and the [M, N] bf16 mask operand of RELU_MASK is 44 % of the masked dgrad's
+   * traffic; the bit record is 1/16 of it.  `aux` = uint32 [M, N / 32] (ldaux in words), bit ((e >> 1) + 16 (e & 1))
+   * of word n / 32 for column n = 32 (n / 32) + e.  tcgen05 path only: bf16 C, N % 64 == 0, no residual / accumulate
+   * (svla_gemm returns SVLA_ERR_BAD_SHAPE otherwise; callers fall back to RELU / RELU_MASK). */
+  SVLA_EPI_RELU_BITS = 4,   /* C = relu(acc + bias), aux bit = (C > 0)   (written) */
+  SVLA_EPI_MASK_BITS = 5    /* C = acc * aux bit                          (read)    */
 } svla_epilogue;
 
 typedef struct {

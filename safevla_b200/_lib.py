@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsafevla_b200.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_GELU = 0, 1, 2, 3
+EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_GELU, EPI_RELU_BITS, EPI_MASK_BITS = 0, 1, 2, 3, 4, 5
 ATTN_FULL, ATTN_TRAJ_CAUSAL, ATTN_T5_BIAS = 0, 1, 2
 PPO_NSCALARS = 16
 

@@ -52,9 +52,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void mbar_arrive_release(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// register re-balancing between the warpgroups of a CTA (warps 0-3 control, 4-7 and 8-11 compute)
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// register re-balancing between the warpgroups of a CTA: reg_inc / reg_dec (tc_common.cuh)
 __device__ __forceinline__ float ex2_approx(float x) {  // 2^x (ex2.approx.ftz: 2^-inf = +0)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -13,6 +13,19 @@ extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream str
   SVLA_CHECK_ARG(d->M >= 0 && d->N >= 0 && d->K >= 0, "negative dimension");
   SVLA_CHECK_ARG(!d->accumulate || d->dtypeC == SVLA_F32, "accumulate needs an fp32 C");
   SVLA_CHECK_ARG(d->epilogue != SVLA_EPI_RELU_MASK || d->aux, "RELU_MASK needs aux");
+  if (d->epilogue == SVLA_EPI_RELU_BITS || d->epilogue == SVLA_EPI_MASK_BITS) {
+    // bit-record epilogues exist on the tensor-core kernels only (64-column block epilogue)
+    SVLA_CHECK_ARG(d->aux && (reinterpret_cast<uintptr_t>(d->aux) & 7) == 0 && d->ldaux % 2 == 0 && d->ldaux * 32 >= d->N,
+                   "bit-record epilogue: aux = uint32 [M, N / 32], 8-byte aligned rows");
+    svla_gemm_desc e = *d;  // the kernels' own aux checks are about the bf16 / fp32 mask operand
+    e.aux = nullptr;
+    if (d->impl == 1 || d->dtypeC != SVLA_BF16 || d->residual || d->accumulate || d->colsum_a || d->N % 64 != 0 ||
+        d->transA || !svla_gemm_tc_supported(&e)) {
+      svla_set_error("svla_gemm: bit-record epilogue needs the tcgen05 path (bf16 C, N %% 64 == 0, no residual / "
+                     "accumulate): M=%d N=%d K=%d", d->M, d->N, d->K);
+      return SVLA_ERR_BAD_SHAPE;
+    }
+  }
   SVLA_CHECK_ARG(d->lda >= (d->transA ? d->M : d->K), "lda too small");
   SVLA_CHECK_ARG(d->ldb >= (d->transB ? d->K : d->N), "ldb too small");
   SVLA_CHECK_ARG(d->ldc >= d->N, "ldc too small");

@@ -82,6 +82,9 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int total_work = g.tiles_m * g.tiles_n * g.splits;
   const int kb_total = (g.K + BK - 1) / BK;
 
+  if (warp < kEpiWarp0) {
+    reg_dec<40>();  // 4 x 40 + 8 x 232 registers per thread-quad slot: the epilogue warps hold a tile of side operand
+  }
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
@@ -151,6 +154,7 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
+    reg_inc<232>();
     // ================================ epilogue ================================
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns this warp drains
@@ -169,7 +173,7 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int wn = w + gridDim.x;  // the tile this warp drains next: its side operand is requested early
       const int next_m0 = wn < total_work ? ((wn / g.tiles_n) % g.tiles_m) * BM + q * 32 : -1;
       const int next_nt0 = (wn % g.tiles_n) * BN;
-      if (staged && g.dbg == 0) side_prefetch_first(pre, g, tm * BM + q * 32, tn * BN + cb, lane);
+      if (staged && g.dbg == 0) side_prefetch_first(pre, g, tm * BM + q * 32, tn * BN + cb, lane, (ce - cb) / 32);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (g.dbg == 1) {

@@ -131,6 +131,9 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const int kb_total = (g.K + BK - 1) / BK;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
+  if (warp < kEpiWarp0) {
+    reg_dec<40>();  // 4 x 40 + 8 x 232 registers per thread-quad slot: the epilogue warps hold a tile of side operand
+  }
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
     if (elect_one()) {
@@ -208,6 +211,7 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
   } else if (warp >= kEpiWarp0) {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
+    reg_inc<232>();
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
     int acc = 0;
@@ -226,7 +230,7 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const int wn = w + num_clusters;  // the tile this warp drains next: its side operand is requested early
       const int next_m0 = wn < total_work ? ((wn / g.tiles_n) % tiles_m2) * 256 + (int)rank * BM + q * 32 : -1;
       const int next_nt0 = (wn % g.tiles_n) * BN2;
-      if (staged) side_prefetch_first(pre, g, m0, tn * BN2 + cb, lane);  // in flight while the MMAs finish
+      if (staged) side_prefetch_first(pre, g, m0, tn * BN2 + cb, lane, 4);  // in flight while the MMAs finish
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (g.dbg == 1) {

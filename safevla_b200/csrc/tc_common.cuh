@@ -210,15 +210,20 @@ __device__ __forceinline__ void piece_load(uint32_t stg_s, int lane, int j, floa
 
 
 // ---- side-operand prefetch ------------------------------------------------------------------------------
-// The ReLU-mask operand / residual tile does not depend on the accumulator, so its global loads are issued one
-// 32-column chunk ahead of their use (across tile boundaries too, and for the first tile before the wait for the
-// accumulator): the epilogue no longer exposes a DRAM round trip per chunk.  (Two chunks ahead was measured slower:
-// the extra registers spill.)  Only the first side operand in application order (aux, residual) of bf16 tiles is
-// prefetched; anything else takes the synchronous stage_in path.
+// The ReLU-mask operand / residual tile does not depend on the accumulator, so its global loads are issued a WHOLE
+// TILE ahead of their use: while chunk c of this tile is processed, the registers it just released are refilled with
+// chunk c of the tile this warp drains next (for the first tile: before the wait for the accumulator).  A K = 512
+// tile takes ~0.6 us, i.e. about one DRAM round trip, whereas a chunk takes ~150 ns -- the one-chunk-ahead prefetch
+// of round 1 still exposed most of the latency (FFN-down dgrad with the ReLU mask 0.69 PF/s, K = 512 residual
+// launches 0.50 PF/s against 1.1-1.2 PF/s without a side operand).  The 64 registers per lane come from the control
+// warps (setmaxnreg in the kernels).  Only the first side operand in application order (aux, residual) of bf16
+// tiles is prefetched; anything else takes the synchronous stage_in path.
 struct SidePre {
-  uint4 v[4];  // this lane's 16-byte pieces of the next chunk to be consumed
-  int valid;
+  uint4 v[4][4];  // [chunk][piece]: this lane's 16-byte pieces of the four 32-column chunks of the next tile
+  int valid;      // bit c: chunk c is in registers
 };
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ int side_pick(const TcArgs& g, const void** base, long long* ld) {
   if (g.splits > 1 || g.dtypeC != SVLA_BF16) return 0;
   if (g.epilogue == SVLA_EPI_RELU_MASK && g.aux) { *base = g.aux; *ld = g.ldaux; return 1; }
@@ -241,13 +246,17 @@ __device__ __forceinline__ void side_commit(uint32_t stg_s, const uint4* v, int 
   for (int p = 0; p < 4; ++p) sts128(stg_s + stg_off<false>(p * 8 + (lane >> 2), lane & 3), v[p]);
   __syncwarp();
 }
-// chunk 0 of a warp's first tile, issued by the caller BEFORE it waits for the accumulator
-__device__ __forceinline__ void side_prefetch_first(SidePre& pre, const TcArgs& g, int m0, int n0, int lane) {
+// every chunk of a warp's first tile, issued by the caller BEFORE it waits for the accumulator
+__device__ __forceinline__ void side_prefetch_first(SidePre& pre, const TcArgs& g, int m0, int n0, int lane, int nch) {
   const void* base = nullptr;
   long long ld = 0;
-  if (pre.valid || !side_pick(g, &base, &ld) || n0 >= g.N) return;
-  side_fetch(pre.v, base, ld * 2, (long long)n0 * 2, m0, g.M, lane);
-  pre.valid = 1;
+  if (pre.valid || !side_pick(g, &base, &ld)) return;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c < nch && n0 + c * 32 < g.N) {
+      side_fetch(pre.v[c], base, ld * 2, (long long)(n0 + c * 32) * 2, m0, g.M, lane);
+      pre.valid |= 1 << c;
+    }
 }
 
 // columns [c_begin, c_end) of the tile for the 32 rows starting at m0
@@ -286,13 +295,12 @@ __device__ __forceinline__ void epilogue_staged_impl(const TcArgs& g, const CUte
     else if (EPI == SVLA_EPI_RELU_MASK) { side = 1; side_base = g.aux; side_ld = g.ldaux; }
     else if (RES) { side = 2; side_base = g.residual; side_ld = g.ldr; }
   }
-#pragma unroll 1
-  for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk) {
+#pragma unroll
+  for (chunk = 0; chunk < 4; ++chunk) {  // unrolled: the prefetch registers are indexed by the chunk
+    const int c0 = c_begin + chunk * 32;
+    if (c0 >= c_end) break;  // warp-uniform (two chunks per warp for 128-wide tiles)
     const int n0 = ntile0 + c0;
-    if (n0 >= g.N) {  // warp-uniform
-      pre.valid = 0;
-      break;
-    }
+    if (n0 >= g.N) break;    // warp-uniform
     uint8_t* stg = stg0 + (kBufs == 2 ? (chunk & 1) * 2048 : 0);
     const uint32_t stg_s = smem_u32(stg);
     if (g.tma_store) {  // the bulk store that last read this buffer must have finished reading it
@@ -304,16 +312,14 @@ __device__ __forceinline__ void epilogue_staged_impl(const TcArgs& g, const CUte
     }
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);
-    if (side) {  // this chunk's side operand: registers -> staging; then request the next chunk of the stream
-      if (!pre.valid) side_fetch(pre.v, side_base, side_ld * ES, (long long)n0 * ES, m0, g.M, lane);  // cold start
-      side_commit(stg_s, pre.v, lane);
-      pre.valid = 0;
-      if (c0 + 32 < c_end && n0 + 32 < g.N) {
-        side_fetch(pre.v, side_base, side_ld * ES, (long long)(n0 + 32) * ES, m0, g.M, lane);
-        pre.valid = 1;
-      } else if (next_m0 >= 0 && next_ntile0 + c_begin < g.N) {
-        side_fetch(pre.v, side_base, side_ld * ES, (long long)(next_ntile0 + c_begin) * ES, next_m0, g.M, lane);
-        pre.valid = 1;
+    if (side) {  // this chunk's side operand: registers -> staging; then request the same chunk of the NEXT tile
+      if (!((pre.valid >> chunk) & 1))
+        side_fetch(pre.v[chunk], side_base, side_ld * ES, (long long)n0 * ES, m0, g.M, lane);  // cold start
+      side_commit(stg_s, pre.v[chunk], lane);
+      pre.valid &= ~(1 << chunk);
+      if (next_m0 >= 0 && next_ntile0 + c0 < g.N) {
+        side_fetch(pre.v[chunk], side_base, side_ld * ES, (long long)(next_ntile0 + c0) * ES, next_m0, g.M, lane);
+        pre.valid |= 1 << chunk;
       }
     }
     // bias of the 32 columns: one coalesced load (lane l holds column l), broadcast by shuffles after the wait --
@@ -438,6 +444,10 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
       b0 = __ldg(g.bias + n0 + lane);
       b1 = __ldg(g.bias + n0 + 32 + lane);
     }
+    // bit record of this lane's row: two words (columns n0 .. n0 + 31, n0 + 32 .. n0 + 63)
+    uint32_t* bits_p = reinterpret_cast<uint32_t*>(const_cast<void*>(g.aux)) + (long long)(m0 + lane) * g.ldaux + (n0 >> 5);
+    uint2 mb = make_uint2(0u, 0u);
+    if (EPI == SVLA_EPI_MASK_BITS && m0 + lane < g.M) mb = __ldg(reinterpret_cast<const uint2*>(bits_p));
     tmem_wait_ld();
     if (g.alpha != 1.f) {
 #pragma unroll
@@ -472,13 +482,28 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]), __uint_as_float(r[jj * 8 + 2 * e + 1]));
-      if (EPI == SVLA_EPI_RELU) {
+      if (EPI == SVLA_EPI_RELU || EPI == SVLA_EPI_RELU_BITS) {
         const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], z);
       }
+      if (EPI == SVLA_EPI_RELU_BITS) {
+        // non-negative bf16 pairs: (w + 0x7FFF7FFF) has bit 15 / 31 set iff the low / high element is > 0; sixteen
+        // shift-in steps leave element e of the chunk at bit (e >> 1) + 16 (e & 1)
+        uint32_t& acc = j < 4 ? mb.x : mb.y;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc = (acc >> 1) | ((w[e] + 0x7FFF7FFFu) & 0x80008000u);
+      }
+      if (EPI == SVLA_EPI_MASK_BITS) {
+        const uint32_t word = j < 4 ? mb.x : mb.y;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] &= ((word >> (jj * 4 + e)) & 0x00010001u) * 0xFFFFu;
+      }
       sts128(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), u);
     }
+    if (EPI == SVLA_EPI_RELU_BITS && m0 + lane < g.M) *reinterpret_cast<uint2*>(bits_p) = mb;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
@@ -507,7 +532,10 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
     else SVLA_EPI_CALL(-1, false, false, false);
   } else {
     const bool blk = g.tma_store && !rs && !ac && e != SVLA_EPI_RELU_MASK && g.dbg != 9;  // 64-column blocks
-    if (ac) SVLA_EPI_CALL(-1, false, false, false);
+    if (e == SVLA_EPI_RELU_BITS && b) epilogue_block64<SVLA_EPI_RELU_BITS, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (e == SVLA_EPI_RELU_BITS) epilogue_block64<SVLA_EPI_RELU_BITS, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (e == SVLA_EPI_MASK_BITS) epilogue_block64<SVLA_EPI_MASK_BITS, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (ac) SVLA_EPI_CALL(-1, false, false, false);
     else if (blk && e == SVLA_EPI_NONE && b) epilogue_block64<SVLA_EPI_NONE, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
     else if (blk && e == SVLA_EPI_NONE && !b) epilogue_block64<SVLA_EPI_NONE, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
     else if (blk && e == SVLA_EPI_RELU && b) epilogue_block64<SVLA_EPI_RELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);

@@ -256,7 +256,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
         assert bias.dtype == torch.float32 and bias.numel() >= N
     if residual is not None:
         d.residual, d.ldr, d.dtypeR = ptr(residual), residual.stride(0), dt(residual)
-    if aux is not None:
+    if aux is not None and epilogue in (L.EPI_RELU_BITS, L.EPI_MASK_BITS):
+        assert aux.dtype == torch.int32 and aux.shape[0] >= M and aux.shape[1] * 32 >= N  # one bit per element
+        d.aux, d.ldaux, d.dtypeAux = ptr(aux), aux.stride(0), dt(out)
+    elif aux is not None:
         d.aux, d.ldaux, d.dtypeAux = ptr(aux), aux.stride(0), dt(aux)
     d.epilogue, d.accumulate, d.alpha, d.impl = epilogue, int(accumulate), alpha, impl
     if colsum_a is not None:  # bias gradient of the same linear, accumulated (trans_a launches only)

@@ -17,7 +17,8 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from ._lib import ATTN_FULL, ATTN_T5_BIAS, ATTN_TRAJ_CAUSAL, EPI_NONE, EPI_RELU, EPI_RELU_MASK, RowMap
+from ._lib import (ATTN_FULL, ATTN_T5_BIAS, ATTN_TRAJ_CAUSAL, EPI_MASK_BITS, EPI_NONE, EPI_RELU, EPI_RELU_BITS,
+                   EPI_RELU_MASK, RowMap)
 from .params import D, DC_BINS, DC_HIDDEN, DC_MAX, DC_MIN, DC_SIGMA, DEC_FF, FF, ParamLayout, T5Layout
 
 H, DH = 8, 64
@@ -96,8 +97,21 @@ class Tower:
             b = b.reshape(-1)
         return self._gemm(x, w, out, trans_b=True, bias=b, epilogue=epi, residual=residual)
 
-    def _lin_bwd(self, dy, x, wname, bname, *, wshape=None, dx=None, aux=None, residual=None, count=1):
-        """dW += dy^T x ; db += colsum(dy) ; dx = dy W [* relu'(aux)] [+ residual]."""
+    def _relu_fwd(self, x, wname, bname, out, *, wshape=None, keep=True):
+        """out = relu(x W^T + b).  Returns (out, bits): on the bf16 tensor-core path the epilogue also records one bit
+        per element (out > 0) for the backward -- the masked dgrad then reads 1/16 of the bytes it would re-read from
+        `out` (those K = 512 launches are HBM-bound); bits is None where the plain ReLU epilogue ran."""
+        M, N = x.shape[0], out.shape[1]
+        if keep and x.dtype == torch.bfloat16 and M >= 256 and N % 64 == 0 and N >= 256:
+            bits = torch.empty(M, N // 32, device=self.dev, dtype=torch.int32)
+            w = self.W.w(wname, wshape, 1, dtype=x.dtype)
+            self._gemm(x, w, out, trans_b=True, bias=self.W.p(bname).reshape(-1), epilogue=EPI_RELU_BITS, aux=bits)
+            return out, bits
+        return self._lin_fwd(x, wname, bname, out, wshape=wshape, epi=EPI_RELU), None
+
+    def _lin_bwd(self, dy, x, wname, bname, *, wshape=None, dx=None, aux=None, residual=None, count=1, bits=None):
+        """dW += dy^T x ; db += colsum(dy) ; dx = dy W [* relu'(aux)] [+ residual].  `bits`: the bit record written by
+        `_relu_fwd` for the activation `aux` (used instead of re-reading it)."""
         gw = self.W.g(wname, wshape, count)
         if gw.dim() != 2:
             gw = gw.view(gw.shape[0], -1)
@@ -107,8 +121,11 @@ class Tower:
             w = self.W.w(wname, wshape, count, dtype=dy.dtype)
             if w.dim() != 2:
                 w = w.view(w.shape[0], -1)
-            self._gemm(dy, w, dx, trans_b=False, aux=aux, epilogue=EPI_RELU_MASK if aux is not None else EPI_NONE,
-                     residual=residual)
+            if bits is not None and residual is None:
+                self._gemm(dy, w, dx, trans_b=False, aux=bits, epilogue=EPI_MASK_BITS)
+            else:
+                self._gemm(dy, w, dx, trans_b=False, aux=aux, epilogue=EPI_RELU_MASK if aux is not None else EPI_NONE,
+                           residual=residual)
         return dx
 
     # ------------------------------------------------------------------ encoder
@@ -125,17 +142,18 @@ class Tower:
         cam_tokens = ["visual_sensor_token_raw_navigation_camera", "visual_sensor_token_raw_manipulation_camera"]
         for c in range(self.C):
             Mv = Rc * TOK
-            c1 = self._lin_fwd(vis[c], ve + "visual_compressor.0.weight", ve + "visual_compressor.0.bias",
-                               self._new(Mv, D), wshape=(D, 384), epi=EPI_RELU)
-            c2 = self._lin_fwd(c1, ve + "visual_compressor.2.weight", ve + "visual_compressor.2.bias",
-                               self._new(Mv, D), wshape=(D, D), epi=EPI_RELU)
+            c1, c1b = self._relu_fwd(vis[c], ve + "visual_compressor.0.weight", ve + "visual_compressor.0.bias",
+                                     self._new(Mv, D), wshape=(D, 384), keep=keep)
+            c2, c2b = self._relu_fwd(c1, ve + "visual_compressor.2.weight", ve + "visual_compressor.2.bias",
+                                     self._new(Mv, D), wshape=(D, D), keep=keep)
             a1 = self._lin_fwd(c2, ve + "visual_adapter.0.weight", ve + "visual_adapter.0.bias", self._new(Mv, D))
             mean, rstd = self._new(Mv, dtype=torch.float32), self._new(Mv, dtype=torch.float32)
             ops.layernorm_fwd(a1, W.p(ve + "visual_adapter.1.weight"), W.p(ve + "visual_adapter.1.bias"), seq,
                               token=W.p(ve + cam_tokens[c]), relu=True, eps=LN_EPS,
                               ymap=RowMap(TOK, S, 1 + TOK * c), mean=mean, rstd=rstd, rows=Mv)
             if keep:
-                st.t.update({f"c1_{c}": c1, f"c2_{c}": c2, f"a1_{c}": a1, f"vmean_{c}": mean, f"vrstd_{c}": rstd})
+                st.t.update({f"c1_{c}": c1, f"c2_{c}": c2, f"a1_{c}": a1, f"vmean_{c}": mean, f"vrstd_{c}": rstd,
+                             f"c1b_{c}": c1b, f"c2b_{c}": c2b})
         Mt = Rc * L
         t1 = self._lin_fwd(text_hidden, ve + "text_adapter.0.weight", ve + "text_adapter.0.bias", self._new(Mt, D))
         tmean, trstd = self._new(Mt, dtype=torch.float32), self._new(Mt, dtype=torch.float32)
@@ -158,7 +176,7 @@ class Tower:
                 m1, r1 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
                 x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Ms, D),
                                        eps=LN_EPS, mean=m1, rstd=r1)
-                hf = self._lin_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Ms, FF), epi=EPI_RELU)
+                hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Ms, FF), keep=keep)
                 s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Ms, D), residual=x1)
                 m2, r2 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
                 x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Ms, D),
@@ -166,7 +184,7 @@ class Tower:
                 if keep:
                     st.t.update({f"x_{l}": x, f"qkv_{l}": qkv, f"ao_{l}": ao, f"lse_{l}": lse, f"s1_{l}": s1,
                                  f"m1_{l}": m1, f"r1_{l}": r1, f"x1_{l}": x1, f"hf_{l}": hf, f"s2_{l}": s2,
-                                 f"m2_{l}": m2, f"r2_{l}": r2})
+                                 f"m2_{l}": m2, f"r2_{l}": r2, f"hfb_{l}": hfb})
                 x = x2
             else:
                 # Only output token 0 is consumed (allenact_dino_transformer.py:708): K/V for every token,
@@ -183,7 +201,7 @@ class Tower:
                 m1, r1 = self._new(Rc, dtype=torch.float32), self._new(Rc, dtype=torch.float32)
                 x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Rc, D),
                                        eps=LN_EPS, mean=m1, rstd=r1)
-                hf = self._lin_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Rc, FF), epi=EPI_RELU)
+                hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Rc, FF), keep=keep)
                 s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Rc, D), residual=x1)
                 m2, r2 = self._new(Rc, dtype=torch.float32), self._new(Rc, dtype=torch.float32)
                 x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Rc, D),
@@ -191,7 +209,7 @@ class Tower:
                 if keep:
                     st.t.update({f"x_{l}": x, f"kv_{l}": kv, f"q0_{l}": q0, f"ao_{l}": ao, f"lse_{l}": lse,
                                  f"s1_{l}": s1, f"m1_{l}": m1, f"r1_{l}": r1, f"x1_{l}": x1, f"hf_{l}": hf,
-                                 f"s2_{l}": s2, f"m2_{l}": m2, f"r2_{l}": r2})
+                                 f"s2_{l}": s2, f"m2_{l}": m2, f"r2_{l}": r2, f"hfb_{l}": hfb})
                 return x2, (st if keep else None)
         cls = self._new(Rc, D)
         ops.copy_rows(x, cls, Rc, D, smap=RowMap(1, S, 0))
@@ -221,7 +239,7 @@ class Tower:
             ds2 = ops.layernorm_bwd(dy, t[f"s2_{l}"], W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), t[f"m2_{l}"],
                                     t[f"r2_{l}"], self._new(rows, D), W.g(p + "norm2.weight"), W.g(p + "norm2.bias"))
             dhf = self._lin_bwd(ds2, t[f"hf_{l}"], p + "linear2.weight", p + "linear2.bias", dx=self._new(rows, FF),
-                                aux=t[f"hf_{l}"])
+                                aux=t[f"hf_{l}"], bits=t.get(f"hfb_{l}"))
             dx1 = self._lin_bwd(dhf, t[f"x1_{l}"], p + "linear1.weight", p + "linear1.bias", dx=self._new(rows, D),
                                 residual=ds2)
             del dhf, ds2
@@ -268,9 +286,9 @@ class Tower:
                                     W.g(ve + "visual_adapter.1.bias"), relu=True, dymap=RowMap(TOK, S, 1 + TOK * c),
                                     dtoken=W.g(ve + cam_tokens[c]), rows=Mv)
             dc2 = self._lin_bwd(da1, t[f"c2_{c}"], ve + "visual_adapter.0.weight", ve + "visual_adapter.0.bias",
-                                dx=self._new(Mv, D), aux=t[f"c2_{c}"])
+                                dx=self._new(Mv, D), aux=t[f"c2_{c}"], bits=t.get(f"c2b_{c}"))
             dc1 = self._lin_bwd(dc2, t[f"c1_{c}"], ve + "visual_compressor.2.weight", ve + "visual_compressor.2.bias",
-                                wshape=(D, D), dx=self._new(Mv, D), aux=t[f"c1_{c}"])
+                                wshape=(D, D), dx=self._new(Mv, D), aux=t[f"c1_{c}"], bits=t.get(f"c1b_{c}"))
             self._lin_bwd(dc1, vis[c], ve + "visual_compressor.0.weight", ve + "visual_compressor.0.bias",
                           wshape=(D, 384))
             del da1, dc2, dc1

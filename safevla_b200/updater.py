@@ -23,8 +23,9 @@ import torch.distributed as dist
 from . import _lib as L
 from . import ops
 from .lagrange import Lagrange
+from .misc import nvtx_range
 from .model import ACTOR, COST, CRITIC, B200SafeActorCritic
-from .parallel import TAIL, allreduce_arena
+from .parallel import TAIL
 from .storage import B200RolloutStorage
 
 
@@ -79,6 +80,7 @@ class PPOLagUpdater:
                 tw.W.grads = model.grad_arena
             model.attach_grads()
         self.launches = 0
+        self._pending = []  # (tower, async all-reduce handle) of gradient slices already in flight
 
     # ------------------------------------------------------------------
     def _hp(self, R: int) -> L.PpoHparams:
@@ -95,14 +97,16 @@ class PPOLagUpdater:
         K = storage.K
         assert K == self.lagrange.K == m.K, "storage, model and cost limits must agree on the number of cost channels"
         # the bootstrap rows (value / cost-value predictions of the step after the rollout) are already in the arena
-        storage.before_updates(next_value=storage.value_preds[T], next_c_value=None,
-                               use_gae=True, gamma=c.gamma, tau=c.gae_lambda,
-                               normalize_advantage=c.normalize_advantage, process_group=self.pg)
+        with nvtx_range("update/gae"):
+            storage.before_updates(next_value=storage.value_preds[T], next_c_value=None,
+                                   use_gae=True, gamma=c.gamma, tau=c.gae_lambda,
+                                   normalize_advantage=c.normalize_advantage, process_group=self.pg)
         adv_t = storage.norm_adv_targ if c.normalize_advantage else storage.adv_targ
         c_adv_1 = storage.c_norm_adv_targ if c.normalize_advantage else storage.c_adv_targ
         c_adv_k = storage.c_norm_adv_targ_k if c.normalize_advantage else storage.c_adv_targ_k
         obs = {k: v[:T] for k, v in storage.observations.items()}
-        rc = m.prepare(obs, T, N)
+        with nvtx_range("update/prepare"):
+            rc = m.prepare(obs, T, N)
         pa = storage.prev_actions[:T]
         mk = storage.masks[:T].view(T, N)
         grad_towers = (CRITIC, COST) if c.stage == 0 else (ACTOR, CRITIC)
@@ -114,8 +118,9 @@ class PPOLagUpdater:
             for idx in (ACTOR, CRITIC, COST):
                 if idx not in grad_towers and not c.evaluate_unused_towers:
                     continue
-                o, st = m.tower_forward(idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR),
-                                        want_values=(idx != ACTOR))
+                with nvtx_range(f"update/rep{rep}/fwd/tower{idx}"):
+                    o, st = m.tower_forward(idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR),
+                                            want_values=(idx != ACTOR))
                 outs[idx], states[idx] = o, st
             if c.stage == 0 and K == 1:
                 scal, _, dv, dcv = ops.ppo_lag_fwd_bwd(
@@ -123,6 +128,7 @@ class PPOLagUpdater:
                     outs[COST]["values"], storage.c_returns[:T], None, hp,
                     old_values=storage.value_preds[:T], old_c_values=storage.c_value_preds[:T])
                 m.tower_backward(CRITIC, states[CRITIC], None, dv)
+                self._reduce_tower_async(CRITIC)
                 m.tower_backward(COST, states[COST], None, dcv)
             elif c.stage == 0:
                 # K cost channels: the cost critic's head emits [T, N, K]; its loss is the SUM over channels of the
@@ -135,6 +141,7 @@ class PPOLagUpdater:
                                                         tnk(storage.c_returns_k[:, :T]), None, hp,
                                                         old_c_values=tnk(storage.c_value_preds_k[:, :T]))
                 m.tower_backward(CRITIC, states[CRITIC], None, dv)
+                self._reduce_tower_async(CRITIC)
                 m.tower_backward(COST, states[COST], None, dcv)
                 scal = torch.cat([scal[0:4], scal_c[4:5], scal[5:]])  # [0] value-critic total, [4] cost-critic total
             else:
@@ -145,10 +152,14 @@ class PPOLagUpdater:
                     outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, adv_t,
                     c_adv, outs[CRITIC]["values"], storage.returns[:T], None, None,
                     lam, hp, old_values=storage.value_preds[:T])
-                m.tower_backward(ACTOR, states[ACTOR], dl, None)
-                m.tower_backward(CRITIC, states[CRITIC], None, dv)
+                with nvtx_range(f"update/rep{rep}/bwd/tower{ACTOR}"):
+                    m.tower_backward(ACTOR, states[ACTOR], dl, None)
+                self._reduce_tower_async(ACTOR)  # the actor's slice crosses NVLink while the critic's backward runs
+                with nvtx_range(f"update/rep{rep}/bwd/tower{CRITIC}"):
+                    m.tower_backward(CRITIC, states[CRITIC], None, dv)
             del states
-            self._reduce_clip_step(storage, last=(rep == c.update_repeats - 1))
+            with nvtx_range(f"update/rep{rep}/reduce_clip_adam"):
+                self._reduce_clip_step(storage, last=(rep == c.update_repeats - 1))
         # lambda <- proj(lambda + Adam step on (Jc - d)); Jc from the (all-reduced) finished-episode costs
         cost_pair = self.comm[-self.TAIL:-self.TAIL + 2 * K] if self.world > 1 else storage.cost_sum_cnt
         self.lagrange.update_from_sum_count(cost_pair)
@@ -185,12 +196,43 @@ class PPOLagUpdater:
                          "step": self.tower_steps[ti]}
         return out
 
+    def _reduce_tower_async(self, idx: int):
+        """Data parallel only: starts the all-reduce of ONE tower's gradient slice on NCCL's stream as soon as that
+        tower's backward has been enqueued, so it overlaps the next tower's backward; `_reduce_clip_step` waits for it
+        and reduces what is left.  The towers are independent, so nothing later writes into the slice."""
+        if self.world == 1:
+            return
+        from .params import TOWERS
+        a, b = self.model.layout.tower_range[TOWERS[idx]]
+        self._pending.append((idx, dist.all_reduce(self.comm[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)))
+
     def _reduce_clip_step(self, storage: B200RolloutStorage, last: bool):
         m, c = self.model, self.cfg
         n = m.layout.total
         prescale = 1.0
-        if self.world > 1:  # the one collective per step
-            prescale = allreduce_arena(self.comm, n, storage.cost_sum_cnt if last else None, self.pg)
+        if self.world > 1:
+            # Only the towers this stage trains carry gradients (the third tower's slice is all zeros: a third of the
+            # arena is never sent); slices already in flight are waited for, the rest + the packed cost scalars of the
+            # last repeat go in one more collective.
+            from .params import TOWERS
+            done = {i for i, _ in self._pending}
+            rest = [i for i in m.trainable_towers if i not in done]
+            lo = min(m.layout.tower_range[TOWERS[i]][0] for i in rest)
+            hi = max(m.layout.tower_range[TOWERS[i]][1] for i in rest)
+            if last:  # tail: [sum of finished-episode costs, count] per cost channel -> lambda identical on all ranks
+                k = storage.cost_sum_cnt.numel()
+                self.comm[n:n + self.TAIL].zero_()
+                self.comm[n:n + k].copy_(storage.cost_sum_cnt)
+                if hi == n:
+                    hi = n + self.TAIL  # the cost tower's slice is adjacent to the tail: one collective
+                else:
+                    self._pending.append((-1, dist.all_reduce(self.comm[n:n + self.TAIL], op=dist.ReduceOp.SUM,
+                                                              group=self.pg, async_op=True)))
+            dist.all_reduce(self.comm[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            for _, work in self._pending:
+                work.wait()
+            self._pending.clear()
+            prescale = 1.0 / self.world
         self.adam_step += 1
         hp = L.AdamHparams(c.lr, c.betas[0], c.betas[1], c.eps, c.max_grad_norm, prescale, self.adam_step, 1)
         # torch.optim.Adam skips parameters whose .grad is None: only the towers this stage trains are

@@ -807,3 +807,37 @@ def test_attention_split_operand_matches_fp64(dev, mode, S, B, adjacent):
     _ops().attn_bwd(mode, q, k, v, o, do, dq, dk, dv, lse, B, S, traj=traj, split=3)
     for name, got, exp in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dv, vr.grad)):
         assert relerr(got, exp) < 3e-5, (name, relerr(got, exp))
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 512), (117 * 70, 512, 384), (300, 256, 64), (4096 + 77, 2048, 512)])
+def test_gemm_relu_bit_record_epilogues(dev, M, N, K):
+    """RELU_BITS writes relu(x W^T + b) and one bit per element; MASK_BITS applies that record in the dgrad: both
+    bit-identical to the RELU / RELU_MASK epilogues they replace (the record is 1/16 of the mask operand's bytes)."""
+    L = _L()
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(dev, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev, torch.bfloat16)
+    b = torch.randn(N, generator=g).to(dev)
+    ref = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    _ops().gemm(x, w, ref, bias=b, epilogue=L.EPI_RELU)
+    out = torch.empty_like(ref)
+    bits = torch.full((M, N // 32), -1, device=dev, dtype=torch.int32)
+    _ops().gemm(x, w, out, bias=b, epilogue=L.EPI_RELU_BITS, aux=bits)
+    assert torch.equal(out, ref)
+    # decode the record: element e of word n / 32 sits at bit (e >> 1) + 16 (e & 1)
+    e = torch.arange(32, device=dev)
+    pos = (e >> 1) + 16 * (e & 1)
+    dec = ((bits.to(torch.int64).unsqueeze(-1) >> pos) & 1).reshape(M, N).bool()
+    assert torch.equal(dec, ref > 0)
+    dy = torch.randn(M, N, generator=g).to(dev, torch.bfloat16)   # a dgrad whose OUTPUT has the activation's shape
+    w2 = (torch.randn(K, N, generator=g) / K ** 0.5).to(dev, torch.bfloat16)  # dX[M, N] = dY2[M, K] W2[K, N]
+    dy2 = torch.randn(M, K, generator=g).to(dev, torch.bfloat16)
+    d_ref, d_out = torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    _ops().gemm(dy2, w2, d_ref, trans_b=False, aux=ref, epilogue=L.EPI_RELU_MASK)
+    _ops().gemm(dy2, w2, d_out, trans_b=False, aux=bits, epilogue=L.EPI_MASK_BITS)
+    assert torch.equal(d_out, d_ref)
+    del dy
+    # shapes the tensor-core path does not take are refused loudly (callers fall back to RELU / RELU_MASK)
+    small = torch.empty(8, N, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        _ops().gemm(x[:8], w, small, bias=b, epilogue=L.EPI_RELU_BITS, aux=bits[:8].contiguous())
