@@ -268,7 +268,8 @@ def run_b200(args, wl, name):
     scan = scan_roofline(dev, pk) if world == 1 else None
     K = wl.get("K", 1)  # cost channels
     model = B200SafeActorCritic(A, C, precision=args.precision, seed=0, device=dev, chunk_rows=args.chunk_rows,
-                                extras="off", verify_dedupe=False, num_cost_channels=K)
+                                extras="off", verify_dedupe=False, num_cost_channels=K, dropout=args.dropout,
+                                dropout_seed=1234)
     cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS, cost_limit=2.31964 if K == 1 else (2.31964,) * K)
     upd = PPOLagUpdater(model, cfg)
     ro = make_rollout(RolloutSpec(T, n_local, A, C, prompt_tokens=wl["L"], seed=1234, num_cost_channels=K), rank=rank,
@@ -402,7 +403,8 @@ def run_b200(args, wl, name):
                    "prompt_tokens": wl["L"], "cost_channels": K, "update_repeats": UPDATE_REPEATS,
                    "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (1.06 GB of observations per rank-rollout at N=64)",
-                   "precision": args.precision, "chunk_rows": args.chunk_rows},
+                   "precision": args.precision, "chunk_rows": args.chunk_rows,
+                   "dropout": args.dropout},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": storage.h2d_bytes(),
                 "d2h_bytes_per_step": (16 + K) * 4, "ms_per_step": t_e2e * 1e3},
         "gpu_launches": int(launches),
@@ -437,6 +439,8 @@ def main():
     ap.add_argument("--workload", default="cfg2_64env_128step", choices=list(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "bf16x6"])
     ap.add_argument("--chunk-rows", type=int, default=4096)
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="training-mode dropout of the fusion block (reference: 0.1); 0 = the parity configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--ref-device", default="cpu", help="--impl reference only: cpu (the reference arm) or cuda")

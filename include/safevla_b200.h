@@ -158,6 +158,25 @@ int svla_hl_gauss_fwd_bwd(svla_ctx* ctx, const float* logits, long long ldl, con
  * Dense path (tensor-core bound): building blocks of the three towers
  * ====================================================================================== */
 
+/* Training-mode dropout (nn.TransformerEncoderLayer p = 0.1 in the fusion block, allenact_dino_transformer.py:545-552;
+ * SURVEY.md fact 8).  Masks are counter-based (Philox4x32-7, csrc/philox.cuh): element (row, col) of a site is kept
+ * iff the 16-bit uniform drawn from (seed, step, site, row0 + row, col / 8)[col % 8] >= round(p * 65536), kept values
+ * are scaled by 1 / (1 - p).  Nothing is stored: forward, backward, recompute and svla_dropout_rows (below) regenerate
+ * the same mask from the same five numbers. */
+typedef struct {
+  float p;                  /* drop probability, 0 <= p < 1; 0 = off */
+  unsigned long long seed;
+  unsigned int site;        /* which dropout of the network (tower, layer, position) */
+  unsigned int step;        /* update repeat / rollout counter */
+  unsigned int row0;        /* global row of the tensor's first row (row chunks of one logical tensor) */
+} svla_dropout;
+
+/* out[r, c] = keep(r, c) ? x[r, c] / (1 - p) : 0 over [rows, cols] (row strides ldx / ldo; in place allowed).  The
+ * stand-alone form of every fused dropout site: dropout1 / dropout2 of the encoder layer around the residual adds, the
+ * gradient masks of the backward, and -- applied to ones -- the mask itself (tests). */
+int svla_dropout_rows(svla_ctx* ctx, const void* x, int dtype_x, long long ldx, void* out, int dtype_out, long long ldo,
+                      long long rows, int cols, const svla_dropout* drop, svla_stream stream);
+
 typedef enum {
   SVLA_EPI_NONE = 0,
   SVLA_EPI_RELU = 1,        /* C = relu(acc + bias) */
@@ -187,6 +206,9 @@ typedef struct {
   int impl;                         /* 0 auto, 1 SIMT fp32-FMA, 2 tcgen05 (bf16 operands) */
   float* colsum_a;                  /* transA only (weight gradients, A = dY stored [K, M]): colsum_a[m] += sum_k A[k, m],
                                        the bias gradient of the same nn.Linear; NULL = not wanted */
+  const svla_dropout* dropout;      /* RELU_BITS only: C = dropout(relu(acc + bias)) -- the FFN dropout of the encoder
+                                       layer fused into linear1's epilogue; the bit record then carries relu AND keep,
+                                       so the backward is MASK_BITS with alpha = 1 / (1 - p).  NULL = none */
 } svla_gemm_desc;
 
 /* C = epi(alpha * op(A) op(B) + bias) [+ residual] -- every nn.Linear / 1x1 Conv2d forward, dgrad
@@ -233,6 +255,16 @@ typedef enum {
 int svla_attn_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
                   long long ldo, int dtype, float* lse, const int64_t* traj, const float* bias,
                   const int64_t* keymask, int B, int S, int H, int dh, float scale, svla_stream stream);
+/* the same with dropout on the attention probabilities (nn.MultiheadAttention dropout, applied after the softmax
+ * normalisation): warp-specialised tcgen05 kernels only (bf16, S <= 128, modes FULL / TRAJ_CAUSAL); mask rows are
+ * (b * H + h) * 128 + query, columns the keys. */
+int svla_attn_drop_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                       long long ldo, float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,
+                       const svla_dropout* drop, svla_stream stream);
+int svla_attn_drop_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                       const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
+                       const int64_t* traj, int B, int S, int H, int dh, float scale, const svla_dropout* drop,
+                       svla_stream stream);
 int svla_attn_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
                   const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, int dtype,
                   const float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,

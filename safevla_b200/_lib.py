@@ -36,6 +36,11 @@ class AdamHparams(C.Structure):
                 ("zero_grad", C.c_int)]
 
 
+class Dropout(C.Structure):
+    """svla_dropout: counter-based mask spec (p, seed, site, step, row0)."""
+    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("site", C.c_uint), ("step", C.c_uint), ("row0", C.c_uint)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
                 ("A", c_p), ("lda", c_ll), ("transA", C.c_int),
@@ -46,7 +51,7 @@ class GemmDesc(C.Structure):
                 ("residual", c_p), ("ldr", c_ll), ("dtypeR", C.c_int),
                 ("aux", c_p), ("ldaux", c_ll), ("dtypeAux", C.c_int),
                 ("epilogue", C.c_int), ("accumulate", C.c_int), ("alpha", C.c_float), ("impl", C.c_int),
-                ("colsum_a", c_p)]
+                ("colsum_a", c_p), ("dropout", C.POINTER(Dropout))]
 
 
 class RowMap(C.Structure):
@@ -111,6 +116,11 @@ PROTOTYPES: Dict[str, list] = {
                             C.c_float, c_p],
     "svla_attn_split_bwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_p, c_p, c_p, c_ll, c_p, c_p,
                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
+    "svla_dropout_rows": [c_p, c_p, C.c_int, c_ll, c_p, C.c_int, c_ll, c_ll, C.c_int, C.POINTER(Dropout), c_p],
+    "svla_attn_drop_fwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                           C.c_float, C.POINTER(Dropout), c_p],
+    "svla_attn_drop_bwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_ll, c_p, c_p, C.c_int, C.c_int,
+                           C.c_int, C.c_int, C.c_float, C.POINTER(Dropout), c_p],
     "svla_split_concat": [c_p, c_p, c_ll, c_ll, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.POINTER(C.c_int), c_p],
     "svla_hash_rows": [c_p, c_p, c_ll, C.c_int, c_p, c_p],
     "svla_episode_cost_step": [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p],

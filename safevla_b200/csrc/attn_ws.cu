@@ -73,6 +73,8 @@ struct WsArgs {
   float* lse;
   void* o; long long ldo;                  // forward output (bf16: NP = 1, fp32: NP = 3)
   void* dq; void* dk; void* dv; long long ldd;
+  DropArgs drop;        // dropout on the attention probabilities (thr == 0: off); mask row = drop_row0 + item * 128 + query
+  uint32_t drop_row0;
 };
 
 // 8 consecutive P values of row i (columns c8*8 ..) into the hi (and lo) tile
@@ -264,6 +266,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_ws_fwd_kernel(const __gri
           p[e] = ex2_approx(fmaf(__uint_as_float(r[c8 * 8 + e]), sl2, -mxs));
           s4[e & 3] += p[e];
         }
+        if (MODE == SVLA_ATTN_FULL && a.drop.thr != 0u) {  // normaliser = undropped row sum; P V sees the dropped row
+          const uint32_t keep = dropout_keep8(a.drop, a.drop_row0 + (uint32_t)(w * 128 + i), (uint32_t)c8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) p[e] = ((keep >> e) & 1u) ? p[e] * a.drop.scale : 0.f;
+        }
         store_p8_parts<NP>(sP, i, c8, p);
       }
       const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
@@ -428,6 +435,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
       tmem_wait_ld();
       // P in place of S (fp32); key columns >= S (zero-filled K / V rows) and masked pairs give exactly 0
       float d4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t kb[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // keep bits of this lane's 64 columns (dropout on P)
+      if (MODE == SVLA_ATTN_FULL && a.drop.thr != 0u) {  // the decoder (TRAJ_CAUSAL) has no dropout
+        kb[0] = kb[1] = 0u;
+#pragma unroll
+        for (int l8 = 0; l8 < 8; ++l8)
+          kb[l8 >> 2] |= dropout_keep8(a.drop, a.drop_row0 + (uint32_t)(w * 128 + i), (uint32_t)(hf * 8 + l8)) << ((l8 & 3) * 8);
+      }
+      const float dsc = (MODE == SVLA_ATTN_FULL) ? a.drop.scale : 1.f;  // 1 when dropout is off
       if (MODE == SVLA_ATTN_TRAJ_CAUSAL) {
         const int my_traj = traj[i];
 #pragma unroll
@@ -436,7 +451,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
           const bool ok = col <= i && traj[col] == my_traj && i < S;
           const float p = ok ? ex2_approx(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
           rs[e] = __float_as_uint(p);
-          d4[e & 3] = fmaf(p, __uint_as_float(rp[e]), d4[e & 3]);
+          const float pm = ((kb[e >> 5] >> (e & 31)) & 1u) ? p * dsc : 0.f;
+          d4[e & 3] = fmaf(pm, __uint_as_float(rp[e]), d4[e & 3]);
         }
       } else {
 #pragma unroll
@@ -447,14 +463,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
             for (int e = 0; e < 32; ++e) {
               const float p = ex2_approx(fmaf(__uint_as_float(rs[c * 32 + e]), sl2, -lse2));
               rs[c * 32 + e] = __float_as_uint(p);
-              d4[e & 3] = fmaf(p, __uint_as_float(rp[c * 32 + e]), d4[e & 3]);
+              const float pm = ((kb[c] >> e) & 1u) ? p * dsc : 0.f;
+              d4[e & 3] = fmaf(pm, __uint_as_float(rp[c * 32 + e]), d4[e & 3]);
             }
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const float p = (col0 + e < S) ? ex2_approx(fmaf(__uint_as_float(rs[c * 32 + e]), sl2, -lse2)) : 0.f;
               rs[c * 32 + e] = __float_as_uint(p);
-              d4[e & 3] = fmaf(p, __uint_as_float(rp[c * 32 + e]), d4[e & 3]);
+              const float pm = ((kb[c] >> e) & 1u) ? p * dsc : 0.f;
+              d4[e & 3] = fmaf(pm, __uint_as_float(rp[c * 32 + e]), d4[e & 3]);
             }
           }
         }
@@ -476,9 +494,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
         for (int e2 = 0; e2 < 4; ++e2) {
           const int e = l8 * 8 + 2 * e2;
           const float p0 = __uint_as_float(rs[e]), p1 = __uint_as_float(rs[e + 1]);
-          const __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1);
-          const __nv_bfloat162 hd = __floats2bfloat162_rn(p0 * (__uint_as_float(rp[e]) - delta),
-                                                          p1 * (__uint_as_float(rp[e + 1]) - delta));
+          // P~ = P * keep / (1 - p) feeds dV = P~^T dO; dS = P~ dP - P delta (delta = rowsum(P~ dP))
+          const float m0 = ((kb[e >> 5] >> (e & 31)) & 1u) ? p0 * dsc : 0.f;
+          const float m1 = ((kb[(e + 1) >> 5] >> ((e + 1) & 31)) & 1u) ? p1 * dsc : 0.f;
+          const __nv_bfloat162 hp = __floats2bfloat162_rn(m0, m1);
+          const __nv_bfloat162 hd = __floats2bfloat162_rn(fmaf(m0, __uint_as_float(rp[e]), -p0 * delta),
+                                                          fmaf(m1, __uint_as_float(rp[e + 1]), -p1 * delta));
           pw[e2] = *reinterpret_cast<const uint32_t*>(&hp);
           dw[e2] = *reinterpret_cast<const uint32_t*>(&hd);
         }
@@ -812,8 +833,9 @@ bool svla_attn_ws_supported(int mode, int dtype, int S, int dh, long long ld, lo
          ld % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) && al16(v) && al16(o);
 }
 
-int svla_attn_ws_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
-                     long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st) {
+static int attn_ws_fwd_impl(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                            long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                            const svla_dropout* drop, cudaStream_t st) {
   WsMaps m{};
   int rc;
   if ((rc = svla_make_tmap3_bf16(ctx, q, (long long)H * DH, S, B, ld, DH, TS, &m.q[0]))) return rc;
@@ -821,14 +843,22 @@ int svla_attn_ws_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
   if ((rc = svla_make_tmap3_bf16(ctx, v, (long long)H * DH, S, B, ld, DH, TS, &m.v[0]))) return rc;
   WsArgs a{};
   a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = lse; a.o = o; a.ldo = ldo;
+  a.drop = make_drop_args(drop);
+  a.drop_row0 = drop ? drop->row0 : 0u;
   const int grid = std::min(B * H, ctx->sm_count);
   if (mode == SVLA_ATTN_FULL) return launch_fwd<SVLA_ATTN_FULL, 1>(m, a, grid, st);
   return launch_fwd<SVLA_ATTN_TRAJ_CAUSAL, 1>(m, a, grid, st);
 }
 
-int svla_attn_ws_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* d_o,
-                     long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse, const int64_t* traj,
-                     int B, int S, int H, float scale, cudaStream_t st) {
+int svla_attn_ws_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                     long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st) {
+  return attn_ws_fwd_impl(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, nullptr, st);
+}
+
+static int attn_ws_bwd_impl(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                            const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
+                            const int64_t* traj, int B, int S, int H, float scale, const svla_dropout* drop,
+                            cudaStream_t st) {
   WsMaps m{};
   int rc;
   if ((rc = svla_make_tmap3_bf16(ctx, q, (long long)H * DH, S, B, ld, DH, TS, &m.q[0]))) return rc;
@@ -838,9 +868,46 @@ int svla_attn_ws_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
   WsArgs a{};
   a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = const_cast<float*>(lse);
   a.dq = dq; a.dk = dk; a.dv = dv; a.ldd = ldd;
+  a.drop = make_drop_args(drop);
+  a.drop_row0 = drop ? drop->row0 : 0u;
   const int grid = std::min(B * H, ctx->sm_count);
   if (mode == SVLA_ATTN_FULL) return launch_bwd<SVLA_ATTN_FULL>(m, a, grid, st);
   return launch_bwd<SVLA_ATTN_TRAJ_CAUSAL>(m, a, grid, st);
+}
+
+int svla_attn_ws_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* d_o,
+                     long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse, const int64_t* traj,
+                     int B, int S, int H, float scale, cudaStream_t st) {
+  return attn_ws_bwd_impl(ctx, mode, q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale, nullptr, st);
+}
+
+extern "C" int svla_attn_drop_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                                  void* o, long long ldo, float* lse, const int64_t* traj, int B, int S, int H, int dh,
+                                  float scale, const svla_dropout* drop, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && q && k && v && o, "NULL argument");
+  SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
+  SVLA_CHECK_ARG(svla_attn_ws_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, o),
+                 "attention with dropout: bf16, S <= 128, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
+  SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
+  SVLA_CHECK_ARG(mode == SVLA_ATTN_FULL || !drop || drop->p == 0.f, "dropout exists for mode FULL (the fusion block) only");
+  if (B <= 0) return SVLA_OK;
+  return attn_ws_fwd_impl(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, drop, as_stream(stream));
+}
+
+extern "C" int svla_attn_drop_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                                  const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd,
+                                  const float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,
+                                  const svla_dropout* drop, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && q && k && v && d_o && dq && dk && dv && lse, "NULL argument");
+  SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
+  SVLA_CHECK_ARG(svla_attn_ws_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, d_o) && ldd % 8 == 0 && al16(dq) &&
+                     al16(dk) && al16(dv),
+                 "attention with dropout: bf16, S <= 128, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
+  SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
+  SVLA_CHECK_ARG(mode == SVLA_ATTN_FULL || !drop || drop->p == 0.f, "dropout exists for mode FULL (the fusion block) only");
+  if (B <= 0) return SVLA_OK;
+  return attn_ws_bwd_impl(ctx, mode, q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale, drop,
+                          as_stream(stream));
 }
 
 // ---- split-operand (parity-grade) entry points: x_lo = x_hi + lo_off elements (svla_split_concat, axis 1, {0, 1})

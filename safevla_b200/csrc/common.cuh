@@ -48,6 +48,24 @@ extern unsigned long long g_svla_launches;
 
 static inline cudaStream_t as_stream(svla_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- dropout spec -> device arguments (csrc/philox.cuh) ---------------------------------------
+#include "philox.cuh"
+static inline bool svla_dropout_ok(const svla_dropout* d) { return !d || (d->p >= 0.f && d->p < 1.f); }
+static inline DropArgs make_drop_args(const svla_dropout* d) {
+  DropArgs a{};
+  if (d && d->p > 0.f) {
+    a.thr = (uint32_t)(d->p * 65536.0 + 0.5);
+    a.scale = 1.f / (1.f - d->p);
+    a.key0 = (uint32_t)(d->seed & 0xFFFFFFFFull);
+    a.key1 = (uint32_t)(d->seed >> 32);
+    a.site = d->site;
+    a.step = d->step;
+  } else {
+    a.scale = 1.f;
+  }
+  return a;
+}
+
 // ---- dtype helpers -----------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

@@ -291,6 +291,28 @@ __global__ void __launch_bounds__(256) scale_by_kernel(float* __restrict__ x, lo
     x[i] *= f;
 }
 
+
+// ---- stand-alone dropout ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) dropout_rows_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ out,
+                                                           long long ldo, long long rows, int cols, DropArgs d,
+                                                           uint32_t row0) {
+  const int g8 = cols >> 3;  // column groups of eight: one Philox call each
+  const long long total = rows * g8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / g8;
+    const int cg = (int)(i - r * g8);
+    const uint32_t keep = dropout_keep8(d, row0 + (uint32_t)r, (uint32_t)cg);
+    const float4 a = load4<TI>(x + r * ldx + cg * 8), b = load4<TI>(x + r * ldx + cg * 8 + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? v[e] * d.scale : 0.f;
+    store4<TO>(out + r * ldo + cg * 8, make_float4(o[0], o[1], o[2], o[3]));
+    store4<TO>(out + r * ldo + cg * 8 + 4, make_float4(o[4], o[5], o[6], o[7]));
+  }
+}
+
 }  // namespace
 
 extern "C" int svla_scale_by(svla_ctx* ctx, float* x, long long n, const float* scale_dev, svla_stream stream) {
@@ -309,6 +331,20 @@ extern "C" int svla_scale_by(svla_ctx* ctx, float* x, long long n, const float* 
     else if (dtA == SVLA_BF16 && dtB == SVLA_BF16) { using TA_ = __nv_bfloat16; using TB_ = __nv_bfloat16; __VA_ARGS__; } \
     else { svla_set_error("bad dtype"); return SVLA_ERR_BAD_ARG; }                      \
   } while (0)
+
+extern "C" int svla_dropout_rows(svla_ctx* ctx, const void* x, int dtype_x, long long ldx, void* out, int dtype_out,
+                                 long long ldo, long long rows, int cols, const svla_dropout* drop, svla_stream stream) {
+  SVLA_CHECK_ARG(ctx && x && out && drop, "NULL argument");
+  SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
+  SVLA_CHECK_ARG(rows >= 0 && cols >= 0 && cols % 8 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "cols must be a multiple of 8");
+  if (rows == 0 || cols == 0) return SVLA_OK;
+  const DropArgs d = make_drop_args(drop);
+  DISPATCH2E(dtype_x, TI, dtype_out, TO,
+             (dropout_rows_kernel<TI, TO><<<ew_grid(ctx, rows * (cols / 8), 256), 256, 0, as_stream(stream)>>>(
+                 reinterpret_cast<const TI*>(x), ldx, reinterpret_cast<TO*>(out), ldo, rows, cols, d, drop->row0)));
+  SVLA_LAUNCH_CHECK();
+  return SVLA_OK;
+}
 
 extern "C" int svla_swiglu_fwd(svla_ctx* ctx, const void* ab, void* g, int dtype, long long rows, int F,
                                svla_stream stream) {

@@ -13,6 +13,9 @@ extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream str
   SVLA_CHECK_ARG(d->M >= 0 && d->N >= 0 && d->K >= 0, "negative dimension");
   SVLA_CHECK_ARG(!d->accumulate || d->dtypeC == SVLA_F32, "accumulate needs an fp32 C");
   SVLA_CHECK_ARG(d->epilogue != SVLA_EPI_RELU_MASK || d->aux, "RELU_MASK needs aux");
+  SVLA_CHECK_ARG(!d->dropout || d->dropout->p == 0.f || d->epilogue == SVLA_EPI_RELU_BITS,
+                 "fused dropout exists for the RELU_BITS epilogue only (use svla_dropout_rows elsewhere)");
+  SVLA_CHECK_ARG(svla_dropout_ok(d->dropout), "dropout p must be in [0, 1)");
   if (d->epilogue == SVLA_EPI_RELU_BITS || d->epilogue == SVLA_EPI_MASK_BITS) {
     // bit-record epilogues exist on the tensor-core kernels only (64-column block epilogue)
     SVLA_CHECK_ARG(d->aux && (reinterpret_cast<uintptr_t>(d->aux) & 7) == 0 && d->ldaux % 2 == 0 && d->ldaux * 32 >= d->N,

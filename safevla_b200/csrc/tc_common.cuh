@@ -108,6 +108,8 @@ struct TcArgs {
   float* asum;     // bias gradient fused into a weight-gradient launch (gemm_tc2.cu), or NULL
   float* asum_ws;  // its split-K partials
   int tma_store;
+  DropArgs drop;      // RELU_BITS: dropout after the ReLU (thr == 0: off)
+  uint32_t drop_row0;
   int dbg;  // SVLA_TC_DBG experiments: 1 = skip the epilogue entirely, 2 = TMEM loads only (no global stores),
             // 9 = 32-column chunks instead of the 64-column block epilogue (A/B switch used for the same-box comparison)
 };
@@ -479,13 +481,23 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
       const int jj = j & 3;
       uint4 u;
       __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+      const float dsc = (EPI == SVLA_EPI_RELU_BITS) ? g.drop.scale : 1.f;  // 1 / (1 - p) of the fused dropout (fp32)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]), __uint_as_float(r[jj * 8 + 2 * e + 1]));
+        h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]) * dsc, __uint_as_float(r[jj * 8 + 2 * e + 1]) * dsc);
       if (EPI == SVLA_EPI_RELU || EPI == SVLA_EPI_RELU_BITS) {
         const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], z);
+      }
+      if (EPI == SVLA_EPI_RELU_BITS && g.drop.thr != 0u) {
+        // FFN dropout of the encoder layer: slot j holds columns n0 + 8 j .. + 8 of this lane's row = one Philox group
+        const uint32_t keep = dropout_keep8(g.drop, g.drop_row0 + (uint32_t)(m0 + lane), (uint32_t)((n0 >> 3) + j));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t& w = *reinterpret_cast<uint32_t*>(&h[e]);
+          w &= (((keep >> (2 * e)) & 1u) * 0x0000FFFFu) | (((keep >> (2 * e + 1)) & 1u) * 0xFFFF0000u);
+        }
       }
       if (EPI == SVLA_EPI_RELU_BITS) {
         // non-negative bf16 pairs: (w + 0x7FFF7FFF) has bit 15 / 31 set iff the low / high element is > 0; sixteen

@@ -111,7 +111,7 @@ class B200SafeActorCritic(nn.Module):
                  manip_uuid: str = "manipulation_rgb_dinov2", in_hand_uuid: str = "an_object_is_in_hand",
                  time_step_uuid: str = "time_step", traj_idx_uuid: str = "traj_index", extras: str = "eager",
                  verify_dedupe: bool = True, max_steps: int = 1000, num_cost_channels: int = 1,
-                 critic_type: str = "linear"):
+                 critic_type: str = "linear", dropout: float = 0.0, dropout_seed: int = 0):
         super().__init__()
         # "bf16": bf16 operands on the tcgen05 kernels (the fast path); "fp32": fp32 FMA kernels (CUDA cores);
         # "bf16x3" / "bf16x6": fp32 activations and weights, every tensor-core-shaped product evaluated on the tcgen05
@@ -127,6 +127,15 @@ class B200SafeActorCritic(nn.Module):
         self.K = int(num_cost_channels)
         self.precision = precision
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        # training-mode dropout of the fusion block (reference: p = 0.1 live); 0 = the parity setting.
+        # Counter-based masks: (dropout_seed, dropout_step, site, row, column); dropout_step advances with every
+        # update-mode forward, the rollout-side step (collection under no_grad) runs without dropout.  The frozen T5
+        # encoder runs without dropout (its noise would be an input perturbation shared by the three towers).
+        if not 0.0 <= dropout < 1.0:
+            raise ValueError("dropout must be in [0, 1)")
+        if dropout > 0.0 and precision != "bf16":
+            raise NotImplementedError("dropout > 0 is built on the bf16 tensor-core kernels (precision='bf16')")
+        self.dropout, self.dropout_seed, self.dropout_step = float(dropout), int(dropout_seed), 0
         self.uu = dict(goal=goal_sensor_uuid, rgb=rgb_uuid, manip=manip_uuid, hand=in_hand_uuid,
                        time=time_step_uuid, traj=traj_idx_uuid)
         self.tokenizer = tokenizer or default_synthetic_tokenizer
@@ -161,6 +170,7 @@ class B200SafeActorCritic(nn.Module):
             tw = Tower(TowerWeights(self.layout, pre, self.param_arena, self.grad_arena, self.shadow_arena),
                        num_actions, num_cameras, self.adt, cls_only_last_layer, self.split)
             tw.div_term = self.get_buffer(pre + "time_encoder.div_term")
+            tw.tower_idx = len(self.towers)
             self.towers.append(tw)
         self._anchor = torch.zeros(1, device=self.dev, requires_grad=True)
         self._ctx_cache: Optional[RolloutContext] = None
@@ -332,9 +342,12 @@ class B200SafeActorCritic(nn.Module):
         return 3 * full + pre
 
     def tower_forward(self, idx: int, rc: RolloutContext, prev_actions, masks, *, keep: bool,
-                      want_logits: bool, want_values: bool):
-        """Returns (outputs dict, state for tower_backward or None)."""
+                      want_logits: bool, want_values: bool, dropout_step: Optional[int] = None):
+        """Returns (outputs dict, state for tower_backward or None).  dropout_step: the mask counter of this
+        forward (None: no dropout, e.g. value collection); the backward regenerates the masks from the stored step."""
         tw = self.towers[idx]
+        use_drop = self.dropout > 0.0 and dropout_step is not None
+        tw.drop_p, tw.drop_seed, tw.drop_step = (self.dropout if use_drop else 0.0), self.dropout_seed, dropout_step or 0
         R = rc.T * rc.N
         obs_embed = torch.empty(R, D, device=self.dev, dtype=self.adt)
         chunks = self._chunks(R)
@@ -342,17 +355,18 @@ class B200SafeActorCritic(nn.Module):
         stashes: List[Optional[EncStash]] = []
         for (r0, r1) in chunks:
             vis, th = self._chunk_inputs(rc, r0, r1)
-            cls, st = tw.encoder_fwd(vis, th, rc.L, keep=stash_all)
+            cls, st = tw.encoder_fwd(vis, th, rc.L, keep=stash_all, row_off=r0)
             obs_embed[r0:r1].copy_(cls)
             stashes.append(st)
         out, dstash = tw.decoder_fwd(obs_embed, prev_actions, masks, rc.in_hand, rc.time_step, rc.traj_nt,
                                      rc.perm_tn, rc.T, rc.N, want_logits, want_values, keep)
         state = dict(rc=rc, dec=dstash, enc=stashes, chunks=chunks, prev=prev_actions, masks=masks,
-                     stash_all=stash_all) if keep else None
+                     stash_all=stash_all, drop=(tw.drop_p, tw.drop_step)) if keep else None
         return out, state
 
     def tower_backward(self, idx: int, state, dlogits, dvalues, dfull=None):
         tw, rc = self.towers[idx], state["rc"]
+        tw.drop_p, tw.drop_step = state["drop"]  # the masks of THIS state's forward
         d_obs = tw.decoder_bwd(dlogits, dvalues, state["dec"], state["prev"], state["masks"], rc.in_hand,
                                rc.traj_nt, rc.perm_nt, rc.T, rc.N, dfull=dfull)
         state["dec"] = None
@@ -360,8 +374,8 @@ class B200SafeActorCritic(nn.Module):
             vis, th = self._chunk_inputs(rc, r0, r1)
             st = state["enc"][ci]
             if st is None:  # recompute mode
-                _, st = tw.encoder_fwd(vis, th, rc.L, keep=True)
-            tw.encoder_bwd(d_obs[r0:r1], vis, th, rc.L, st)
+                _, st = tw.encoder_fwd(vis, th, rc.L, keep=True, row_off=r0)
+            tw.encoder_bwd(d_obs[r0:r1], vis, th, rc.L, st, row_off=r0)
             state["enc"][ci] = None
 
     def _tower_backward_autograd(self, idx: int, state, grad_out: Optional[torch.Tensor], dfull=None):
@@ -386,10 +400,14 @@ class B200SafeActorCritic(nn.Module):
         mk = masks.to(self.dev, dtype=torch.float32).reshape(T, N).contiguous()
         grad = torch.is_grad_enabled()
         outs = {}
+        step = None
+        if self.dropout > 0.0 and self.training and grad:  # nn.Module semantics: dropout in train mode only
+            self.dropout_step += 1
+            step = self.dropout_step
         for idx in (ACTOR, CRITIC, COST):
             keep = grad and idx in self.trainable_towers
             o, state = self.tower_forward(idx, rc, pa, mk, keep=keep, want_logits=(idx == ACTOR),
-                                          want_values=(idx != ACTOR))
+                                          want_values=(idx != ACTOR), dropout_step=step)
             t = o["logits"] if idx == ACTOR else o["values"]
             fl = o.get("full_logits")
             if keep and fl is not None:

@@ -168,6 +168,22 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+# ---- dropout -----------------------------------------------------------------------------------
+def dropout_spec(p: float, seed: int, site: int, step: int, row0: int = 0) -> L.Dropout:
+    """svla_dropout: the mask of a site is a pure function of (seed, step, site, row0 + row, column)."""
+    return L.Dropout(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, int(step) & 0xFFFFFFFF,
+                     int(row0) & 0xFFFFFFFF)
+
+
+def dropout_rows(x: torch.Tensor, out: torch.Tensor, drop: L.Dropout, rows=None):
+    """out = keep ? x / (1 - p) : 0 over the 2-D views x / out (row strides respected; in place allowed)."""
+    assert x.dim() == 2 and out.dim() == 2 and x.stride(1) == 1 and out.stride(1) == 1 and x.shape[1] == out.shape[1]
+    rows = x.shape[0] if rows is None else rows
+    check(_lib().svla_dropout_rows(get_ctx(), ptr(x), dt(x), x.stride(0), ptr(out), dt(out), out.stride(0), rows,
+                                   x.shape[1], C.byref(drop), stream_ptr()), "svla_dropout_rows")
+    return out
+
+
 # ---- dense path --------------------------------------------------------------------------------
 # split-operand products (svla_split_concat): (parts of A, parts of B) per product, most significant first
 SPLIT_PATTERNS = {3: ((0, 1, 0), (0, 0, 1)), 6: ((0, 0, 1, 1, 0, 2), (0, 1, 0, 1, 2, 0))}
@@ -209,7 +225,7 @@ def _split_ok(M, N, K, P, trans_a, trans_b, lda, ldb):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, trans_b=True, bias=None,
          residual=None, aux=None, epilogue=L.EPI_NONE, accumulate=False, alpha=1.0, impl=0,
-         M=None, N=None, K=None, lda=None, ldb=None, ldc=None, colsum_a=None, split=0, cache_b=False):
+         M=None, N=None, K=None, lda=None, ldb=None, ldc=None, colsum_a=None, split=0, cache_b=False, dropout=None):
     """out[M,N] = epi(alpha * op(a) op(b) + bias) [+ residual].  a/b/out are 2-D views whose last
     dim is contiguous (row stride = leading dimension).  trans_b=True is the nn.Linear layout.
     split = 3 / 6 (fp32 operands only): the product runs on the bf16 tcgen05 kernels as a sum of 3 / 6 split-operand
@@ -265,6 +281,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a=False, 
     if colsum_a is not None:  # bias gradient of the same linear, accumulated (trans_a launches only)
         assert trans_a and colsum_a.dtype == torch.float32 and colsum_a.numel() >= M
         d.colsum_a = ptr(colsum_a)
+    if dropout is not None:  # RELU_BITS only: dropout fused behind the ReLU
+        assert epilogue == L.EPI_RELU_BITS
+        d.dropout = C.pointer(dropout)
     if PROFILE is None:
         check(_lib().svla_gemm(get_ctx(), C.byref(d), stream_ptr()), "svla_gemm")
         return out
@@ -358,11 +377,17 @@ def _use_split_attn(split, q, mode, S, dh):
     return bool(split) and q.dtype == torch.float32 and S <= 128 and dh == 64 and mode in (L.ATTN_FULL, L.ATTN_TRAJ_CAUSAL)
 
 
-def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bias=None, keymask=None, split=0):
+def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bias=None, keymask=None, split=0,
+             drop=None):
     """q/k/v: 2-D views [B*S, >=H*dh] sharing one row stride (e.g. column slices of a packed qkv buffer).
     split != 0 with fp32 tensors (parity-grade tensor-core mode): the products run as split-bf16 sums on the tcgen05
     kernel (svla_attn_split_fwd) instead of the fp32 CUDA-core kernel."""
     assert q.stride(0) == k.stride(0) == v.stride(0) and q.dtype == k.dtype == v.dtype == o.dtype
+    if drop is not None:  # dropout on the attention probabilities (warp-specialised bf16 kernels only)
+        _timed("attn_fwd", 4.0 * B * H * S * S * dh, (mode, B, S, "bf16+drop"), lambda: check(
+            _lib().svla_attn_drop_fwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), o.stride(0), ptr(lse),
+                                      ptr(traj), B, S, H, dh, scale, C.byref(drop), stream_ptr()), "svla_attn_drop_fwd"))
+        return o
     if _use_split_attn(split, q, mode, S, dh):
         buf, (qo, ko, vo), lo_off, ld = _split_qkv(q, k, v, H, dh)
         base = buf.data_ptr()
@@ -378,9 +403,15 @@ def attn_fwd(mode, q, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, traj=None, bi
     return o
 
 
-def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, traj=None, split=0):
+def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, traj=None, split=0, drop=None):
     assert q.stride(0) == k.stride(0) == v.stride(0) and dq.stride(0) == dk.stride(0) == dv.stride(0)
     assert o.stride(0) == d_o.stride(0)
+    if drop is not None:
+        _timed("attn_bwd", 10.0 * B * H * S * S * dh, (mode, B, S, "bf16+drop"), lambda: check(
+            _lib().svla_attn_drop_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(d_o), d_o.stride(0),
+                                      ptr(dq), ptr(dk), ptr(dv), dq.stride(0), ptr(lse), ptr(traj), B, S, H, dh, scale,
+                                      C.byref(drop), stream_ptr()), "svla_attn_drop_bwd"))
+        return
     if _use_split_attn(split, q, mode, S, dh):
         buf, (qo, ko, vo), lo_off, ld = _split_qkv(q, k, v, H, dh)
         D = H * dh

@@ -76,9 +76,17 @@ class Tower:
         self.critic_type = weights.layout.critic_type
         self.dc_support = (torch.linspace(DC_MIN, DC_MAX, DC_BINS + 1, device=self.dev, dtype=torch.float32)
                            if self.critic_type == "discrete" else None)
+        # training-mode dropout of the fusion block (nn.TransformerEncoderLayer p = 0.1: attention probabilities,
+        # dropout1 / dropout2 before the residual adds, the FFN hidden layer; allenact_dino_transformer.py:545-552).
+        # (p, seed, step) are set per forward / backward by the model; masks are regenerated, never stored.
+        self.drop_p, self.drop_seed, self.drop_step, self.tower_idx = 0.0, 0, 0, 0
         # parity-grade tensor-core mode: fp32 activations / weights, every tensor-core-shaped product evaluated as
         # 3 (or 6) split-bf16 products in one tcgen05 launch (ops.gemm split=); 0 = operands as they are
         self.split = split
+
+    def _site(self, layer: int, kind: int, row0: int):
+        """Dropout spec of site (tower, layer, kind): kind 0 attention probabilities, 1 dropout1, 2 FFN, 3 dropout2."""
+        return ops.dropout_spec(self.drop_p, self.drop_seed, self.tower_idx * 64 + layer * 8 + kind, self.drop_step, row0)
 
     def _gemm(self, a, b, out, **kw):
         if self.split:
@@ -97,19 +105,24 @@ class Tower:
             b = b.reshape(-1)
         return self._gemm(x, w, out, trans_b=True, bias=b, epilogue=epi, residual=residual)
 
-    def _relu_fwd(self, x, wname, bname, out, *, wshape=None, keep=True):
+    def _relu_fwd(self, x, wname, bname, out, *, wshape=None, keep=True, dropout=None):
         """out = relu(x W^T + b).  Returns (out, bits): on the bf16 tensor-core path the epilogue also records one bit
         per element (out > 0) for the backward -- the masked dgrad then reads 1/16 of the bytes it would re-read from
         `out` (those K = 512 launches are HBM-bound); bits is None where the plain ReLU epilogue ran."""
         M, N = x.shape[0], out.shape[1]
-        if keep and x.dtype == torch.bfloat16 and M >= 256 and N % 64 == 0 and N >= 256:
+        bits_ok = x.dtype == torch.bfloat16 and M >= 256 and N % 64 == 0 and N >= 256
+        if dropout is not None and not bits_ok:
+            raise NotImplementedError("fused FFN dropout needs the bf16 tensor-core path (>= 256 token rows per chunk)")
+        if (keep or dropout is not None) and bits_ok:
             bits = torch.empty(M, N // 32, device=self.dev, dtype=torch.int32)
             w = self.W.w(wname, wshape, 1, dtype=x.dtype)
-            self._gemm(x, w, out, trans_b=True, bias=self.W.p(bname).reshape(-1), epilogue=EPI_RELU_BITS, aux=bits)
+            self._gemm(x, w, out, trans_b=True, bias=self.W.p(bname).reshape(-1), epilogue=EPI_RELU_BITS, aux=bits,
+                       dropout=dropout)
             return out, bits
         return self._lin_fwd(x, wname, bname, out, wshape=wshape, epi=EPI_RELU), None
 
-    def _lin_bwd(self, dy, x, wname, bname, *, wshape=None, dx=None, aux=None, residual=None, count=1, bits=None):
+    def _lin_bwd(self, dy, x, wname, bname, *, wshape=None, dx=None, aux=None, residual=None, count=1, bits=None,
+                 alpha=1.0):
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W [* relu'(aux)] [+ residual].  `bits`: the bit record written by
         `_relu_fwd` for the activation `aux` (used instead of re-reading it)."""
         gw = self.W.g(wname, wshape, count)
@@ -122,17 +135,21 @@ class Tower:
             if w.dim() != 2:
                 w = w.view(w.shape[0], -1)
             if bits is not None and residual is None:
-                self._gemm(dy, w, dx, trans_b=False, aux=bits, epilogue=EPI_MASK_BITS)
+                self._gemm(dy, w, dx, trans_b=False, aux=bits, epilogue=EPI_MASK_BITS, alpha=alpha)
             else:
                 self._gemm(dy, w, dx, trans_b=False, aux=aux, epilogue=EPI_RELU_MASK if aux is not None else EPI_NONE,
                            residual=residual)
         return dx
 
     # ------------------------------------------------------------------ encoder
-    def encoder_fwd(self, vis: List[torch.Tensor], text_hidden: torch.Tensor, L: int, keep: bool):
-        """vis[c]: [Rc*84, 384] token-major DINO features (adt); text_hidden [Rc*L, 512] (adt).
+    def encoder_fwd(self, vis: List[torch.Tensor], text_hidden: torch.Tensor, L: int, keep: bool, row_off: int = 0):
+        """vis[c]: [Rc*84, 384] token-major DINO features (adt); text_hidden [Rc*L, 512] (adt); row_off: index of the
+        chunk's first (t, n) row in the rollout (dropout masks are addressed by global rows).
         Returns (cls [Rc, 512] adt, stash or None)."""
         W, adt = self.W, self.adt
+        dp = self.drop_p > 0.0
+        if dp and (adt != torch.bfloat16 or 1 + TOK * self.C + L > 128):
+            raise NotImplementedError("dropout > 0 is built on the bf16 tensor-core kernels with S <= 128 (one camera)")
         Rc = vis[0].shape[0] // TOK
         S = 1 + TOK * self.C + L
         ve = "visual_encoder."
@@ -165,22 +182,38 @@ class Tower:
         Ms = Rc * S
         for l in range(3):
             p = ve + f"fusion_xformer.layers.{l}."
-            last = (l == 2) and self.cls_only
+            last = (l == 2) and self.cls_only and not dp  # with dropout every layer runs in full
             if not last:
                 qkv = self._lin_fwd(x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", self._new(Ms, 3 * D))
                 ao, lse = self._new(Ms, D), self._new(Rc * H * S, dtype=torch.float32)
                 ops.attn_fwd(ATTN_FULL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, lse, Rc, S,
-                             scale=1.0 / math.sqrt(DH), split=self.split)
-                s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Ms, D),
-                                   residual=x)
+                             scale=1.0 / math.sqrt(DH), split=self.split,
+                             drop=self._site(l, 0, row_off * H * 128) if dp else None)
                 m1, r1 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
-                x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Ms, D),
-                                       eps=LN_EPS, mean=m1, rstd=r1)
-                hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Ms, FF), keep=keep)
-                s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Ms, D), residual=x1)
                 m2, r2 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
-                x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Ms, D),
-                                       eps=LN_EPS, mean=m2, rstd=r2)
+                if not dp:
+                    s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
+                                       self._new(Ms, D), residual=x)
+                    x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Ms, D),
+                                           eps=LN_EPS, mean=m1, rstd=r1)
+                    hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Ms, FF), keep=keep)
+                    s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Ms, D), residual=x1)
+                    x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Ms, D),
+                                           eps=LN_EPS, mean=m2, rstd=r2)
+                else:
+                    # x1 = LN(x + dropout1(attn)) ; x2 = LN(x1 + dropout2(W2 dropout(relu(W1 x1)))): the sub-layer
+                    # output is dropped in place and the residual is added inside the LayerNorm kernel; s1 / s2 hold
+                    # the DROPPED sub-layer outputs (the LayerNorm backward re-adds the residual)
+                    s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Ms, D))
+                    ops.dropout_rows(s1, s1, self._site(l, 1, row_off * S))
+                    x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Ms, D),
+                                           res=x, eps=LN_EPS, mean=m1, rstd=r1)
+                    hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Ms, FF), keep=keep,
+                                             dropout=self._site(l, 2, row_off * S))
+                    s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Ms, D))
+                    ops.dropout_rows(s2, s2, self._site(l, 3, row_off * S))
+                    x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Ms, D),
+                                           res=x1, eps=LN_EPS, mean=m2, rstd=r2)
                 if keep:
                     st.t.update({f"x_{l}": x, f"qkv_{l}": qkv, f"ao_{l}": ao, f"lse_{l}": lse, f"s1_{l}": s1,
                                  f"m1_{l}": m1, f"r1_{l}": r1, f"x1_{l}": x1, f"hf_{l}": hf, f"s2_{l}": s2,
@@ -216,9 +249,11 @@ class Tower:
         return cls, (st if keep else None)
 
     def encoder_bwd(self, d_cls: torch.Tensor, vis: List[torch.Tensor], text_hidden: torch.Tensor, L: int,
-                    st: EncStash):
+                    st: EncStash, row_off: int = 0):
         """Accumulates every encoder weight gradient of this chunk into the grad arena."""
         W, adt, t = self.W, self.adt, st.t
+        dp = self.drop_p > 0.0
+        dsc = 1.0 / (1.0 - self.drop_p) if dp else 1.0
         Rc = d_cls.shape[0]
         S = 1 + TOK * self.C + L
         Ms = Rc * S
@@ -226,7 +261,7 @@ class Tower:
         dx = None  # gradient wrt the current layer's output [Ms, D]
         for l in (2, 1, 0):
             p = ve + f"fusion_xformer.layers.{l}."
-            last = (l == 2) and self.cls_only
+            last = (l == 2) and self.cls_only and not dp
             if last:
                 rows = Rc
                 dy = d_cls
@@ -237,17 +272,24 @@ class Tower:
                     ops.copy_rows(d_cls, dx, Rc, D, dmap=RowMap(1, S, 0))
                 dy = dx
             ds2 = ops.layernorm_bwd(dy, t[f"s2_{l}"], W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), t[f"m2_{l}"],
-                                    t[f"r2_{l}"], self._new(rows, D), W.g(p + "norm2.weight"), W.g(p + "norm2.bias"))
-            dhf = self._lin_bwd(ds2, t[f"hf_{l}"], p + "linear2.weight", p + "linear2.bias", dx=self._new(rows, FF),
-                                aux=t[f"hf_{l}"], bits=t.get(f"hfb_{l}"))
+                                    t[f"r2_{l}"], self._new(rows, D), W.g(p + "norm2.weight"), W.g(p + "norm2.bias"),
+                                    res=t[f"x1_{l}"] if dp else None)
+            # gradient of the (dropped) sub-layer output: the residual branch keeps ds2, the FFN branch sees the mask
+            dy2 = ops.dropout_rows(ds2, self._new(rows, D), self._site(l, 3, row_off * S)) if dp else ds2
+            dhf = self._lin_bwd(dy2, t[f"hf_{l}"], p + "linear2.weight", p + "linear2.bias", dx=self._new(rows, FF),
+                                aux=t[f"hf_{l}"], bits=t.get(f"hfb_{l}"), alpha=dsc)
+            del dy2
             dx1 = self._lin_bwd(dhf, t[f"x1_{l}"], p + "linear1.weight", p + "linear1.bias", dx=self._new(rows, D),
                                 residual=ds2)
             del dhf, ds2
             ds1 = ops.layernorm_bwd(dx1, t[f"s1_{l}"], W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), t[f"m1_{l}"],
-                                    t[f"r1_{l}"], self._new(rows, D), W.g(p + "norm1.weight"), W.g(p + "norm1.bias"))
+                                    t[f"r1_{l}"], self._new(rows, D), W.g(p + "norm1.weight"), W.g(p + "norm1.bias"),
+                                    res=t[f"x_{l}"] if dp else None)
             del dx1
-            dao = self._lin_bwd(ds1, t[f"ao_{l}"], p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
+            dy1 = ops.dropout_rows(ds1, self._new(rows, D), self._site(l, 1, row_off * S)) if dp else ds1
+            dao = self._lin_bwd(dy1, t[f"ao_{l}"], p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
                                 dx=self._new(rows, D))
+            del dy1
             x = t[f"x_{l}"]
             wi = W.w(p + "self_attn.in_proj_weight", dtype=adt)
             gwi, gbi = W.g(p + "self_attn.in_proj_weight"), W.g(p + "self_attn.in_proj_bias")
@@ -270,7 +312,8 @@ class Tower:
                 dqkv = self._new(Ms, 3 * D)
                 ops.attn_bwd(ATTN_FULL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], t[f"ao_{l}"], dao,
                              dqkv[:, 0:D], dqkv[:, D:2 * D], dqkv[:, 2 * D:3 * D], t[f"lse_{l}"], Rc, S,
-                             scale=1.0 / math.sqrt(DH), split=self.split)
+                             scale=1.0 / math.sqrt(DH), split=self.split,
+                             drop=self._site(l, 0, row_off * H * 128) if dp else None)
                 dx = self._lin_bwd(dqkv, x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias",
                                    dx=self._new(Ms, D), residual=ds1)
                 del dqkv

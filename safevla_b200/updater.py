@@ -115,12 +115,16 @@ class PPOLagUpdater:
         scal = None
         for rep in range(c.update_repeats):
             outs, states = {}, {}
+            drop_step = None
+            if m.dropout > 0.0:  # fresh masks every repeat, as every reference forward draws new ones
+                m.dropout_step += 1
+                drop_step = m.dropout_step
             for idx in (ACTOR, CRITIC, COST):
                 if idx not in grad_towers and not c.evaluate_unused_towers:
                     continue
                 with nvtx_range(f"update/rep{rep}/fwd/tower{idx}"):
                     o, st = m.tower_forward(idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR),
-                                            want_values=(idx != ACTOR))
+                                            want_values=(idx != ACTOR), dropout_step=drop_step)
                 outs[idx], states[idx] = o, st
             if c.stage == 0 and K == 1:
                 scal, _, dv, dcv = ops.ppo_lag_fwd_bwd(
