@@ -55,15 +55,17 @@ def peaks():
 def ncu_traffic():
     """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/): one representative
     launch (the FFN-up forward GEMM of a 1024-row chunk), next to its algorithmic bytes."""
-    p = os.path.join(ROOT, "profiles", "ncu_r01_traffic.json")
-    if not os.path.exists(p):
-        return {"traffic": None}
-    d = json.load(open(p))
-    d = d.get("gemm_fwd") or d.get("svla_gemm_tc2_kernel<0, 0>")
-    if not d:
-        return {"traffic": None}
-    return {"traffic": d["dram_bytes"], "traffic_launch": d["shape"], "traffic_algorithmic_bytes": d["algorithmic_bytes"],
-            "traffic_src": "profiles/ncu_r01.md"}
+    for rnd in ("r02", "r01"):
+        p = os.path.join(ROOT, "profiles", f"ncu_{rnd}_traffic.json")
+        if not os.path.exists(p):
+            continue
+        d = json.load(open(p))
+        d = d.get("gemm_fwd_bits") or d.get("gemm_fwd") or d.get("svla_gemm_tc2_kernel<0, 0>")
+        if not d:
+            continue
+        return {"traffic": d["dram_bytes"], "traffic_launch": d["shape"],
+                "traffic_algorithmic_bytes": d["algorithmic_bytes"], "traffic_src": f"profiles/ncu_{rnd}.md"}
+    return {"traffic": None}
 
 
 class ClockSampler(threading.Thread):
@@ -421,9 +423,32 @@ def run_b200(args, wl, name):
             v, t, desc = cpu_sample(wl, 1, 1, sample_T=T, sample_N=min(wl["N"], 2))  # warmed: 1 + 1 iterations
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": desc}
-        if not args.no_library_baseline:
-            del upd, storage, model  # the eager baseline needs the HBM the stash held
+        del upd, storage, model  # the legs below need the HBM the stash held
+        torch.cuda.empty_cache()
+        if not args.no_parity_mode and args.precision == "bf16":
+            # the same update in the parity-grade tensor-core mode (fp32 activations / weights, every GEMM and attention
+            # product as three split-bf16 tcgen05 products: logits / values / losses within 1e-4 of the fp32 reference,
+            # tests/test_fastpath_parity_gpu.py), one warm-up + one timed step, device-resident like `value`
+            try:
+                pm = B200SafeActorCritic(A, C, precision="bf16x3", seed=0, device=dev, chunk_rows=args.chunk_rows,
+                                         extras="off", verify_dedupe=False, num_cost_channels=K)
+                pu = PPOLagUpdater(pm, cfg)
+                ps = B200RolloutStorage(T, dev, num_cost_channels=K)
+                ps.load_rollout(ro, vp_host, cvp_host, logp_host)
+
+                def step_parity():
+                    pm._ctx_cache = None
+                    return pu.update(ps)
+                t_par = timed(step_parity, 1, 1)
+                line["parity_mode"] = {"precision": "bf16x3", "dtype": "f32 (3 split-bf16 tcgen05 products per GEMM / attention matmul)",
+                                       "value": samples / t_par, "unit": "samples/s", "ms_per_step": t_par * 1e3,
+                                       "steps": 1, "warmup": 1,
+                                       "tolerance": "logits / values / losses within 1e-4 rel of the fp32 reference goldens"}
+                del pm, pu, ps
+            except Exception as e:  # noqa: BLE001
+                line["parity_mode"] = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
             torch.cuda.empty_cache()
+        if not args.no_library_baseline:
             line["library_baseline"] = library_baseline(wl)
     print(json.dumps(line))
     if world > 1:
@@ -443,6 +468,7 @@ def main():
                     help="training-mode dropout of the fusion block (reference: 0.1); 0 = the parity configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the one-step bf16x3 (parity-grade) measurement")
     ap.add_argument("--ref-device", default="cpu", help="--impl reference only: cpu (the reference arm) or cuda")
     ap.add_argument("--ref-samplers", type=int, default=2, help="--ref-device cuda: samplers in the timed sample")
     ap.add_argument("--ref-tf32", action="store_true", help="--ref-device cuda: allow TF32 tensor-core matmuls")

@@ -449,6 +449,7 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
     // bit record of this lane's row: two words (columns n0 .. n0 + 31, n0 + 32 .. n0 + 63)
     uint32_t* bits_p = reinterpret_cast<uint32_t*>(const_cast<void*>(g.aux)) + (long long)(m0 + lane) * g.ldaux + (n0 >> 5);
     uint2 mb = make_uint2(0u, 0u);
+    uint32_t mbp0[4] = {0u, 0u, 0u, 0u}, mbp1[4] = {0u, 0u, 0u, 0u};
     if (EPI == SVLA_EPI_MASK_BITS && m0 + lane < g.M) mb = __ldg(reinterpret_cast<const uint2*>(bits_p));
     tmem_wait_ld();
     if (g.alpha != 1.f) {
@@ -500,12 +501,23 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
         }
       }
       if (EPI == SVLA_EPI_RELU_BITS) {
-        // non-negative bf16 pairs: (w + 0x7FFF7FFF) has bit 15 / 31 set iff the low / high element is > 0; sixteen
-        // shift-in steps leave element e of the chunk at bit (e >> 1) + 16 (e & 1)
-        uint32_t& acc = j < 4 ? mb.x : mb.y;
+        // non-negative bf16 pairs: (w + 0x7FFF7FFF) has bit 15 / 31 set iff the low / high element is > 0; word wi of
+        // the chunk (elements 2 wi, 2 wi + 1) lands at bits wi and 16 + wi, i.e. element e at (e >> 1) + 16 (e & 1).
+        // Four independent partial records per chunk keep the dependency chains short (the epilogue paces K = 512).
         const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+        if (g.dbg == 6) {  // A/B switch: no packing at all (stores zeros)
+        } else if (g.dbg == 7) {  // A/B switch: the serial shift-in chain
+          uint32_t& acc = j < 4 ? mbp0[0] : mbp1[0];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc = (acc >> 1) | ((w[e] + 0x7FFF7FFFu) & 0x80008000u);
+          for (int e = 0; e < 4; ++e) acc = (acc >> 1) | ((w[e] + 0x7FFF7FFFu) & 0x80008000u);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int wi = jj * 4 + e;  // word index inside the 32-column chunk
+            const uint32_t t = ((w[e] + 0x7FFF7FFFu) >> (15 - wi)) & (0x00010001u << wi);
+            if (j < 4) mbp0[e] |= t; else mbp1[e] |= t;
+          }
+        }
       }
       if (EPI == SVLA_EPI_MASK_BITS) {
         const uint32_t word = j < 4 ? mb.x : mb.y;
@@ -515,7 +527,9 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
       }
       sts128(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), u);
     }
-    if (EPI == SVLA_EPI_RELU_BITS && m0 + lane < g.M) *reinterpret_cast<uint2*>(bits_p) = mb;
+    if (EPI == SVLA_EPI_RELU_BITS && m0 + lane < g.M && g.dbg != 8)
+      *reinterpret_cast<uint2*>(bits_p) = make_uint2((mbp0[0] | mbp0[1]) | (mbp0[2] | mbp0[3]),
+                                                     (mbp1[0] | mbp1[1]) | (mbp1[2] | mbp1[3]));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {

@@ -93,6 +93,14 @@ SHAPES = {
     "gemm_dgrad_mask": (f"dgrad + ReLU mask M={_M} N={_N} K={_K} bf16 (side operand [M, N] bf16)",
                         2 * (_M * _K + _N * _K + 2 * _M * _N)),
     "gemm_wgrad": (f"wgrad M={_N} N={_K} K={_M} fp32 accumulate", 2 * (_M * _N + _M * _K) + 8 * _N * _K),
+    "gemm_fwd_bits": (f"fwd M={_M} N={_N} K={_K} bias+ReLU+bit record bf16", 2 * (_M * _K + _N * _K + _M * _N) + _M * _N // 8),
+    "gemm_dgrad_bits": (f"dgrad masked by the bit record M={_M} N={_N} K={_K} bf16 (side operand [M, N / 32] words)",
+                        2 * (_M * _K + _N * _K + _M * _N) + _M * _N // 8),
+    "gemm_res": (f"fwd M={_M} N={_K} K={_K} bias+residual bf16", 2 * (3 * _M * _K + _K * _K)),
+    "gemm_x3": (f"fwd M={_M} N={_N} K=3x{_K} split-bf16 operands, fp32 out", 2 * 3 * (_M * _K + _N * _K) + 4 * _M * _N),
+    "attn": ("B=1024 S=117 H=8 bf16 (fwd: Q K V O; bwd: Q K V dO dQ dK dV)", None),
+    "split": (f"fp32 [{_M}, {_K}] -> bf16 [{_M}, 3x{_K}]", _M * _K * (4 + 6)),
+    "ln": (f"LayerNorm bwd rows={_M} D=512 bf16 (dy, x in; dx out)", 3 * 2 * _M * 512),
     "gae": ("T=128 N=65536 both streams", 36 * 128 * 65536),
     "loss": ("R=8388608 A=20", (8 * 20 + 44) * 128 * 65536),
     "adam": ("62.9M parameters, fp32 master + bf16 shadow + grad zeroing", (62_900_000 // 64 * 64) * 34),
@@ -115,16 +123,27 @@ def traffic(out, paths):
             v, u = float(r[idx[k]].replace(",", "")), units[idx[k]]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3,
                         "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}.get(u, 1)
-        m = re.search(r"ncu_r\d+_(.+?)_(svla_gemm_tc|attn_tc_fwd|attn_tc_bwd|gae_march|ppo_lag|clip_adam|layernorm_bwd)", p)
+        m = re.search(r"ncu_r\d+_(.+?)_(svla_gemm_tc|attn_tc_fwd|attn_tc_bwd|attn_ws_fwd|attn_ws_bwd_x3|attn_ws_bwd|"
+                      r"split_concat|gae_march|ppo_lag|clip_adam|layernorm_bwd)", p)
         tgt = m.group(1) if m else p
-        key = tgt if tgt.startswith("gemm") or tgt in ("gae", "loss", "adam") else short(r[idx["Kernel Name"]])
+        key = tgt if tgt.startswith("gemm") or tgt in ("gae", "loss", "adam", "split", "ln") else \
+            tgt + ":" + short(r[idx["Kernel Name"]])
         e = {"kernel": short(r[idx["Kernel Name"]]),
              "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
              "ncu_us": val("gpu__time_duration.sum"),
              "tensor_pipe_active_pct": float(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]])}
-        if tgt in SHAPES:
+        if tgt.startswith("attn"):
+            bs, el = 1024 * 117 * 512, (4 if tgt == "attn_x3" else 2)
+            n_t = 4 if "fwd" in e["kernel"] else 7
+            e["shape"] = f"B=1024 S=117 H=8 {'fp32 (hi, lo) operands' if tgt == 'attn_x3' else 'bf16'}"
+            # split mode: operands arrive as two bf16 tensors each (4 B / element), outputs are fp32
+            e["algorithmic_bytes"] = n_t * bs * el
+            e["traffic_over_algorithmic"] = round(e["dram_bytes"] / e["algorithmic_bytes"], 3)
+        elif tgt in SHAPES and SHAPES[tgt][1]:
             e["shape"], e["algorithmic_bytes"] = SHAPES[tgt]
             e["traffic_over_algorithmic"] = round(e["dram_bytes"] / e["algorithmic_bytes"], 3)
+        if e.get("algorithmic_bytes"):
+            e["algorithmic_gbs"] = round(e["algorithmic_bytes"] / e["ncu_us"] / 1e3, 1)
         res[key] = e
     json.dump(res, open(out, "w"), indent=1)
     print(json.dumps(res, indent=1))

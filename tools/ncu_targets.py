@@ -2,7 +2,8 @@
 """Launches each roofline-relevant kernel a few times at its measurement shape, for short `ncu --set full`
 captures (`ncu -k regex:<kernel> -s 2 -c 1 ... python tools/ncu_targets.py <target>`).
 
-targets: gae | loss | adam | ln | gemm_fwd | gemm_dgrad | gemm_wgrad | attn
+targets: gae | loss | adam | ln | gemm_fwd | gemm_fwd_bits | gemm_dgrad | gemm_dgrad_mask | gemm_dgrad_bits | gemm_res |
+         gemm_wgrad | gemm_x3 | attn | attn_x3 | attn_drop | split
 """
 from __future__ import annotations
 
@@ -62,6 +63,26 @@ def main():
             out = torch.empty(M, N, device=dev, dtype=bf)
             bias = torch.zeros(N, device=dev)
             fn = lambda: ops.gemm(a, b, out, trans_b=True, bias=bias, epilogue=L.EPI_RELU)  # noqa: E731
+        elif target == "gemm_fwd_bits":  # linear1 forward: ReLU + one-bit-per-element record
+            a, b = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf)
+            out, bits = torch.empty(M, N, device=dev, dtype=bf), torch.empty(M, N // 32, device=dev, dtype=torch.int32)
+            bias = torch.zeros(N, device=dev)
+            fn = lambda: ops.gemm(a, b, out, trans_b=True, bias=bias, epilogue=L.EPI_RELU_BITS, aux=bits)  # noqa: E731
+        elif target == "gemm_dgrad_bits":  # FFN-down dgrad masked by the bit record (replaces gemm_dgrad_mask on the path)
+            a, b = torch.randn(M, K, device=dev, dtype=bf), torch.randn(K, N, device=dev, dtype=bf)
+            out = torch.empty(M, N, device=dev, dtype=bf)
+            bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (M, N // 32), device=dev, dtype=torch.int32)
+            fn = lambda: ops.gemm(a, b, out, trans_b=False, aux=bits, epilogue=L.EPI_MASK_BITS)  # noqa: E731
+        elif target == "gemm_res":  # out-proj forward: K = 512, N = 512, bias + residual (HBM-bound: 3 KB per row)
+            a, b = torch.randn(M, K, device=dev, dtype=bf), torch.randn(K, K, device=dev, dtype=bf)
+            out, res = torch.empty(M, K, device=dev, dtype=bf), torch.randn(M, K, device=dev, dtype=bf)
+            bias = torch.zeros(K, device=dev)
+            fn = lambda: ops.gemm(a, b, out, trans_b=True, bias=bias, residual=res)  # noqa: E731
+        elif target == "gemm_x3":  # parity-grade mode: fp32 operands as three split-bf16 products in one launch
+            a, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev)
+            out = torch.empty(M, N, device=dev)
+            bias = torch.zeros(N, device=dev)
+            fn = lambda: ops.gemm(a, b, out, trans_b=True, bias=bias, epilogue=L.EPI_RELU, split=3)  # noqa: E731
         elif target == "gemm_dgrad_mask":  # FFN-down dgrad with the fused ReLU mask (side operand = hf)
             a, b = torch.randn(M, K, device=dev, dtype=bf), torch.randn(K, N, device=dev, dtype=bf)
             out, aux = torch.empty(M, N, device=dev, dtype=bf), torch.randn(M, N, device=dev, dtype=bf)
@@ -83,6 +104,20 @@ def main():
         fn = lambda: (ops.attn_fwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, lse, B, S),  # noqa: E731
                       ops.attn_bwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, dqkv[:, :D],
                                    dqkv[:, D:2 * D], dqkv[:, 2 * D:], lse, B, S))
+    elif target in ("attn_x3", "attn_drop"):
+        B, S, D = 1024, 117, 512
+        dt_ = torch.float32 if target == "attn_x3" else bf
+        qkv = torch.randn(B * S, 3 * D, device=dev, dtype=dt_) * 0.5
+        o, do = torch.empty(B * S, D, device=dev, dtype=dt_), torch.randn(B * S, D, device=dev, dtype=dt_)
+        dqkv = torch.empty_like(qkv)
+        lse = torch.empty(B * 8 * S, device=dev)
+        kw = dict(split=3) if target == "attn_x3" else dict(drop=ops.dropout_spec(0.1, 1, 0, 1))
+        fn = lambda: (ops.attn_fwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, lse, B, S, **kw),  # noqa: E731
+                      ops.attn_bwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, dqkv[:, :D],
+                                   dqkv[:, D:2 * D], dqkv[:, 2 * D:], lse, B, S, **kw))
+    elif target == "split":
+        x = torch.randn(119808, 512, device=dev)
+        fn = lambda: ops.split_concat(x, 512, 119808, 512, 1, (0, 1, 0))  # noqa: E731
     else:
         raise SystemExit(f"unknown target {target}")
     e = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
