@@ -34,6 +34,9 @@ import torch  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[1] / configs[2]: 64-env x 128-step ObjectNav rollouts, one camera, 32-token prompt
     "cfg2_64env_128step": dict(T=128, N=64, A=20, C=1, L=32, gflop_per_sample=18.4),
+    # the per-rank shape of configs[2] (64 env over 8 ranks) on ONE GPU: separates small-problem efficiency from
+    # communication when reading the 8-GPU number
+    "cfg3_rank_8env_128step": dict(T=128, N=8, A=20, C=1, L=32, gflop_per_sample=18.4),
     # configs[0] (CPU-runnable correctness gate)
     "cfg1_1env_16step": dict(T=16, N=1, A=6, C=1, L=32, gflop_per_sample=18.4),
     # configs[3] PickupType head, two cameras (S = 201)
@@ -272,7 +275,8 @@ def run_b200(args, wl, name):
     model = B200SafeActorCritic(A, C, precision=args.precision, seed=0, device=dev, chunk_rows=args.chunk_rows,
                                 extras="off", verify_dedupe=False, num_cost_channels=K, dropout=args.dropout,
                                 dropout_seed=1234)
-    cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS, cost_limit=2.31964 if K == 1 else (2.31964,) * K)
+    cfg = PPOLagConfig(update_repeats=UPDATE_REPEATS, cost_limit=2.31964 if K == 1 else (2.31964,) * K,
+                       cuda_graphs=bool(args.cuda_graphs))
     upd = PPOLagUpdater(model, cfg)
     ro = make_rollout(RolloutSpec(T, n_local, A, C, prompt_tokens=wl["L"], seed=1234, num_cost_channels=K), rank=rank,
                       pin=True)
@@ -313,9 +317,14 @@ def run_b200(args, wl, name):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_s = []
+
     def step_resident():
         model._ctx_cache = None  # a new rollout every step: rebuild the observation-derived caches
-        return upd.update(storage)
+        t0 = time.perf_counter()
+        res = upd.update(storage)
+        host_s.append(time.perf_counter() - t0)  # host time to ENQUEUE the step (no sync): launch-bound when ~ step time
+        return res
 
     host_out = torch.empty(16 + 8, pin_memory=True)
 
@@ -354,9 +363,26 @@ def run_b200(args, wl, name):
     l0 = lib.svla_launch_count()
     if rank == 0:  # tools/collect_profiles.sh skips this many launches to capture exactly the timed step under ncu
         print(f"[bench] launches before the timed region: {l0}", file=sys.stderr)
-    ops.PROFILE = {} if rank == 0 else None
+    # Per-launch CUDA events (roofline of the dominant kernel) need the launches on one stream, one after the other.
+    # When the update runs its towers on three streams (small per-rank rollouts) or replays CUDA
+    # graphs, rank 0 times the launches of `steps` extra single-stream, eagerly launched steps right after the timed
+    # region (same kernels, same shapes); otherwise the events are recorded inside the timed region itself.
+    n_local_rows = T * n_local
+    streams_on = (not args.no_tower_streams) and (args.tower_streams or n_local_rows <= 4096)
+    upd.cfg.tower_streams = streams_on
+    graphs = args.cuda_graphs
+    separate = graphs or streams_on
+    ops.PROFILE = {} if (rank == 0 and not separate) else None
     t_res = timed(step_resident, args.steps, 0)
     launches = (lib.svla_launch_count() - l0) // args.steps
+    host_timed = list(host_s[-args.steps:])
+    t_prof = t_res
+    if separate:
+        prev_mode = (upd.cfg.cuda_graphs, upd.cfg.tower_streams)
+        upd.cfg.cuda_graphs, upd.cfg.tower_streams = False, False
+        ops.PROFILE = {} if rank == 0 else None
+        t_prof = timed(step_resident, args.steps, 0)
+        upd.cfg.cuda_graphs, upd.cfg.tower_streams = prev_mode
     prof, ops.PROFILE = ops.profile_summary(ops.PROFILE), None
     # ---- end-to-end metric
     t_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
@@ -378,7 +404,7 @@ def run_b200(args, wl, name):
         # the SURVEY model's algorithmic figure (which also counts work the CLS-only last layer and the prompt
         # de-duplication legitimately skip)
         ex_flops = sum(r["flops"] for r in prof.values()) / args.steps
-        ex_tf = ex_flops / t_res / 1e12
+        ex_tf = ex_flops / t_res / 1e12  # launched FLOPs are the same whether a step is replayed or launched eagerly
         executed = {"achieved": ex_tf * world, "peak": pk["tf_sust"] * world, "frac": ex_tf / pk["tf_sust"],
                     "gflop_per_sample": ex_flops * world / samples / 1e9,
                     "by_kernel": {k: {"tflop_per_step": r["flops"] / args.steps / 1e12,
@@ -393,7 +419,10 @@ def run_b200(args, wl, name):
         peak = pk["tf_sust"]
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "launches_per_step": rec["n"] // args.steps,
-                "share_of_step": rec["ms"] * 1e-3 / (t_res * args.steps), "peak_src": pk["src"] + " (sustained bf16)"}
+                "share_of_step": rec["ms"] * 1e-3 / (t_prof * args.steps), "peak_src": pk["src"] + " (sustained bf16)",
+                "timing": ("CUDA events around every launch inside the timed region" if not separate else
+                           "CUDA events around every launch of single-stream steps right after the timed region "
+                           "(the timed steps run the towers on three streams / replay CUDA graphs)")}
         roof.update(ncu_traffic())
     step_tf = value * wl["gflop_per_sample"] / 1e3
     line = {
@@ -405,11 +434,13 @@ def run_b200(args, wl, name):
                    "prompt_tokens": wl["L"], "cost_channels": K, "update_repeats": UPDATE_REPEATS,
                    "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (1.06 GB of observations per rank-rollout at N=64)",
-                   "precision": args.precision, "chunk_rows": args.chunk_rows,
+                   "precision": args.precision, "chunk_rows": args.chunk_rows, "cuda_graphs": bool(graphs),
+                   "tower_streams": bool(streams_on),
                    "dropout": args.dropout},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": storage.h2d_bytes(),
                 "d2h_bytes_per_step": (16 + K) * 4, "ms_per_step": t_e2e * 1e3},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": 1e3 * sum(host_timed) / max(1, len(host_timed)),
         "clocks": clocks,
         "roofline": roof,
         "step_algorithmic_tflops": {"achieved": step_tf, "peak": pk["tf_sust"] * world,
@@ -466,6 +497,11 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=4096)
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="training-mode dropout of the fusion block (reference: 0.1); 0 = the parity configuration")
+    ap.add_argument("--no-cuda-graphs", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cuda-graphs", action="store_true",
+                    help="replay the forward / loss / backward of every update repeat from a CUDA graph")
+    ap.add_argument("--no-tower-streams", action="store_true", help="run the three towers on one stream")
+    ap.add_argument("--tower-streams", action="store_true", help="three tower streams at any rollout size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-parity-mode", action="store_true", help="skip the one-step bf16x3 (parity-grade) measurement")

@@ -49,6 +49,8 @@ int svla_version(void);
 int svla_sm_count(svla_ctx* ctx);
 /* number of kernels this library has launched in the calling process (monotonic) */
 unsigned long long svla_launch_count(void);
+/* the host replays a CUDA graph that was captured over n launches of this library: keep the counter honest */
+int svla_launch_count_add(unsigned long long n);
 
 /* ======================================================================================
  * Scan / elementwise path (HBM bound)

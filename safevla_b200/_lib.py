@@ -68,6 +68,7 @@ PROTOTYPES: Dict[str, list] = {
     "svla_version": [],
     "svla_sm_count": [c_p],
     "svla_launch_count": [],
+    "svla_launch_count_add": [C.c_ulonglong],
     "svla_gae_dual": [c_p] + [c_p] * 9 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_p],
     "svla_discounted_returns_dual": [c_p] + [c_p] * 9 + [C.c_int, C.c_int, C.c_double, c_p],
     "svla_normalize_advantage": [c_p, c_p, c_p, c_p, c_ll, c_p],
@@ -167,7 +168,7 @@ class _Profiled:
 
 _prof_sink = None
 _SKIP_PROFILE = {"svla_ctx_create", "svla_ctx_destroy", "svla_last_error", "svla_version", "svla_sm_count",
-                 "svla_launch_count", "svla_gemm_which", "svla_set_attn_impl"}
+                 "svla_launch_count", "svla_launch_count_add", "svla_gemm_which", "svla_set_attn_impl"}
 
 
 def profile_start():
@@ -212,17 +213,21 @@ def check(rc: int, what: str = "") -> None:
 
 
 def get_ctx(device: Optional[int] = None) -> int:
-    """One svla_ctx per (process, device)."""
+    """One svla_ctx per (process, device, stream): a context owns the scratch its kernels fold their deterministic
+    reductions in (block partials, tickets, split-K slices), so launches that may run concurrently -- the towers on
+    their own streams -- must not share one."""
     lib = load_library()
     if not torch.cuda.is_available():
         raise RuntimeError("safevla_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     if device is None:
         device = torch.cuda.current_device()
-    if device not in _ctxs:
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ctx = _ctxs.get(key)
+    if ctx is None:
         out = c_p()
         check(lib.svla_ctx_create(int(device), C.byref(out)), "svla_ctx_create")
-        _ctxs[device] = out.value
-    return _ctxs[device]
+        ctx = _ctxs[key] = out.value
+    return ctx
 
 
 def stream_ptr() -> int:

@@ -67,5 +67,9 @@ int svla_ctx_destroy(svla_ctx* ctx) {
 
 int svla_sm_count(svla_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 unsigned long long svla_launch_count(void) { return g_svla_launches; }
+int svla_launch_count_add(unsigned long long n) {  // launches replayed from a CUDA graph captured over this library's calls
+  g_svla_launches += n;
+  return SVLA_OK;
+}
 
 }  // extern "C"

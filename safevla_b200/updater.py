@@ -15,6 +15,7 @@ No autograd, no host sync inside the schedule; scalars for logging are returned 
 from __future__ import annotations
 
 from dataclasses import dataclass
+import ctypes as C
 from typing import Dict, Optional
 
 import torch
@@ -55,6 +56,20 @@ class PPOLagConfig:
     # the reference evaluates all three towers in every forward even when a stage's losses ignore one
     # (separate_actor_critic.py:27-37); keep that by default so samples/s counts the same work
     evaluate_unused_towers: bool = True
+    # Replay the forward + loss + backward of an update repeat from a CUDA graph (captured on the second repeat of a
+    # given (storage, T, N, prompt length) and replayed ever after; the optimizer step stays outside: its bias
+    # corrections are host-side scalars).  The schedule is ~700 C-ABI launches per repeat; once the per-rank problem is
+    # small (64 env over 8 GPUs: 1 024 rows per rank) enqueueing them from Python takes longer than the GPU needs to
+    # run them -- 82.7 ms of host time for an 87.6 ms step, measured -- so data-parallel runs are launch-bound without
+    # it.  Needs dropout off and normalize_advantage off.  Off by default: measured at that per-rank shape the host needs
+    # 39 ms per step to enqueue what the GPU runs in 80 ms, so replay changes the step by 2 % (tools/graph_probe.py);
+    # what is lost there is small-kernel efficiency on the device, which `tower_streams` addresses.
+    cuda_graphs: Optional[bool] = None
+    # Run the three towers on three CUDA streams (they are independent until the loss and again in the backward): the
+    # launch-latency-bound decoder of one tower (~100 small launches forward, ~200 backward) then hides behind the
+    # large encoder GEMMs of another.  Matters when the per-rank problem is small (data-parallel runs).
+    # None = on when the rollout has at most 4 096 rows per rank (above that every launch fills the GPU by itself).
+    tower_streams: Optional[bool] = None
 
 
 class PPOLagUpdater:
@@ -81,6 +96,8 @@ class PPOLagUpdater:
             model.attach_grads()
         self.launches = 0
         self._pending = []  # (tower, async all-reduce handle) of gradient slices already in flight
+        self._graphs: Dict[tuple, dict] = {}  # CUDA graphs of one update repeat, by (storage, shapes, stage)
+        self._streams = None  # one stream per tower, created on first use
 
     # ------------------------------------------------------------------
     def _hp(self, R: int) -> L.PpoHparams:
@@ -113,61 +130,150 @@ class PPOLagUpdater:
         m.set_trainable_towers(grad_towers)
         hp = self._hp(R)
         scal = None
+        use_graph = bool(c.cuda_graphs) and m.dropout == 0.0 and \
+            not c.normalize_advantage and ops.PROFILE is None and L._prof_sink is None
+        ctx = dict(storage=storage, pa=pa, mk=mk, hp=hp, grad_towers=grad_towers, adv_t=adv_t, c_adv_1=c_adv_1,
+                   c_adv_k=c_adv_k, T=T, R=R, K=K)
+        gkey = (id(storage), T, N, rc.L, K, c.stage, c.evaluate_unused_towers, m.precision)
         for rep in range(c.update_repeats):
-            outs, states = {}, {}
             drop_step = None
             if m.dropout > 0.0:  # fresh masks every repeat, as every reference forward draws new ones
                 m.dropout_step += 1
                 drop_step = m.dropout_step
-            for idx in (ACTOR, CRITIC, COST):
-                if idx not in grad_towers and not c.evaluate_unused_towers:
-                    continue
-                with nvtx_range(f"update/rep{rep}/fwd/tower{idx}"):
-                    o, st = m.tower_forward(idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR),
-                                            want_values=(idx != ACTOR), dropout_step=drop_step)
-                outs[idx], states[idx] = o, st
-            if c.stage == 0 and K == 1:
-                scal, _, dv, dcv = ops.ppo_lag_fwd_bwd(
-                    None, None, None, None, None, outs[CRITIC]["values"], storage.returns[:T],
-                    outs[COST]["values"], storage.c_returns[:T], None, hp,
-                    old_values=storage.value_preds[:T], old_c_values=storage.c_value_preds[:T])
-                m.tower_backward(CRITIC, states[CRITIC], None, dv)
-                self._reduce_tower_async(CRITIC)
-                m.tower_backward(COST, states[COST], None, dcv)
-            elif c.stage == 0:
-                # K cost channels: the cost critic's head emits [T, N, K]; its loss is the SUM over channels of the
-                # per-channel SafePPOValue means (inv_count stays 1 / R), evaluated over the R * K flattened entries
-                scal, _, dv, _ = ops.ppo_lag_fwd_bwd(None, None, None, None, None, outs[CRITIC]["values"],
-                                                     storage.returns[:T], None, None, None, hp,
-                                                     old_values=storage.value_preds[:T])
-                tnk = lambda x: x.reshape(K, R).t().contiguous()  # noqa: E731  channel-major -> the head's [R, K]
-                scal_c, _, _, dcv = ops.ppo_lag_fwd_bwd(None, None, None, None, None, None, None, outs[COST]["values"],
-                                                        tnk(storage.c_returns_k[:, :T]), None, hp,
-                                                        old_c_values=tnk(storage.c_value_preds_k[:, :T]))
-                m.tower_backward(CRITIC, states[CRITIC], None, dv)
-                self._reduce_tower_async(CRITIC)
-                m.tower_backward(COST, states[COST], None, dcv)
-                scal = torch.cat([scal[0:4], scal_c[4:5], scal[5:]])  # [0] value-critic total, [4] cost-critic total
+            if use_graph:
+                scal = self._repeat_graphed(gkey, rc, ctx)
             else:
-                c_adv, lam = c_adv_1, self.lagrange.lagrangian_multiplier
-                if K > 1:  # fold the K (advantage, multiplier) pairs into the one pair the fused loss takes
-                    c_adv, lam = ops.combine_cost_advantages(c_adv_k.reshape(K, R), lam)
-                scal, dl, dv, _ = ops.ppo_lag_fwd_bwd(
-                    outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, adv_t,
-                    c_adv, outs[CRITIC]["values"], storage.returns[:T], None, None,
-                    lam, hp, old_values=storage.value_preds[:T])
-                with nvtx_range(f"update/rep{rep}/bwd/tower{ACTOR}"):
-                    m.tower_backward(ACTOR, states[ACTOR], dl, None)
-                self._reduce_tower_async(ACTOR)  # the actor's slice crosses NVLink while the critic's backward runs
-                with nvtx_range(f"update/rep{rep}/bwd/tower{CRITIC}"):
-                    m.tower_backward(CRITIC, states[CRITIC], None, dv)
-            del states
+                scal = self._repeat(rc, ctx, rep, drop_step, overlap=True)
             with nvtx_range(f"update/rep{rep}/reduce_clip_adam"):
                 self._reduce_clip_step(storage, last=(rep == c.update_repeats - 1))
         # lambda <- proj(lambda + Adam step on (Jc - d)); Jc from the (all-reduced) finished-episode costs
         cost_pair = self.comm[-self.TAIL:-self.TAIL + 2 * K] if self.world > 1 else storage.cost_sum_cnt
         self.lagrange.update_from_sum_count(cost_pair)
         return {"loss_scalars": scal, "lambda": self.lagrange.lagrangian_multiplier, "grad_sq_norm": self.sq}
+
+    # ------------------------------------------------------------------ one repeat: forward, loss, backward
+    def _repeat(self, rc, ctx, rep: int, drop_step, overlap: bool):
+        """3-tower forward -> fused loss forward + backward -> tower backwards into the gradient arena.  Returns the
+        loss scalars (device).  overlap: start a tower's gradient all-reduce as soon as its backward is enqueued."""
+        m, c = self.model, self.cfg
+        storage, pa, mk, hp, grad_towers = ctx["storage"], ctx["pa"], ctx["mk"], ctx["hp"], ctx["grad_towers"]
+        adv_t, c_adv_1, c_adv_k, T, R, K = ctx["adv_t"], ctx["c_adv_1"], ctx["c_adv_k"], ctx["T"], ctx["R"], ctx["K"]
+        reduce_async = self._reduce_tower_async if overlap else (lambda idx: None)
+        outs, states = {}, {}
+        main = torch.cuda.current_stream()
+        want_streams = c.tower_streams if c.tower_streams is not None else R <= 4096
+        side = None
+        if want_streams and not torch.cuda.is_current_stream_capturing() and ops.PROFILE is None and L._prof_sink is None:
+            if self._streams is None:
+                self._streams = [torch.cuda.Stream(device=m.dev) for _ in range(3)]
+            side = self._streams  # (per-launch event timing wants one stream: kernels of two towers would overlap)
+
+        def on_tower_stream(idx, fn):
+            """Run fn with tower idx's stream current (ordered after everything enqueued on the main stream so far)."""
+            if side is None:
+                return fn()
+            side[idx].wait_stream(main)
+            with torch.cuda.stream(side[idx]):
+                return fn()
+
+        def join(towers):
+            if side is not None:
+                for idx in towers:
+                    main.wait_stream(side[idx])
+
+        fwd_towers = [idx for idx in (ACTOR, CRITIC, COST) if idx in grad_towers or c.evaluate_unused_towers]
+        for idx in fwd_towers:
+            with nvtx_range(f"update/rep{rep}/fwd/tower{idx}"):
+                o, st = on_tower_stream(idx, lambda idx=idx: m.tower_forward(
+                    idx, rc, pa, mk, keep=idx in grad_towers, want_logits=(idx == ACTOR), want_values=(idx != ACTOR),
+                    dropout_step=drop_step))
+            outs[idx], states[idx] = o, st
+        join(fwd_towers)
+        if c.stage == 0 and K == 1:
+            scal, _, dv, dcv = ops.ppo_lag_fwd_bwd(
+                None, None, None, None, None, outs[CRITIC]["values"], storage.returns[:T],
+                outs[COST]["values"], storage.c_returns[:T], None, hp,
+                old_values=storage.value_preds[:T], old_c_values=storage.c_value_preds[:T])
+            on_tower_stream(CRITIC, lambda: (m.tower_backward(CRITIC, states[CRITIC], None, dv), reduce_async(CRITIC)))
+            on_tower_stream(COST, lambda: m.tower_backward(COST, states[COST], None, dcv))
+            join((CRITIC, COST))
+        elif c.stage == 0:
+            # K cost channels: the cost critic's head emits [T, N, K]; its loss is the SUM over channels of the
+            # per-channel SafePPOValue means (inv_count stays 1 / R), evaluated over the R * K flattened entries
+            scal, _, dv, _ = ops.ppo_lag_fwd_bwd(None, None, None, None, None, outs[CRITIC]["values"],
+                                                 storage.returns[:T], None, None, None, hp,
+                                                 old_values=storage.value_preds[:T])
+            tnk = lambda x: x.reshape(K, R).t().contiguous()  # noqa: E731  channel-major -> the head's [R, K]
+            scal_c, _, _, dcv = ops.ppo_lag_fwd_bwd(None, None, None, None, None, None, None, outs[COST]["values"],
+                                                    tnk(storage.c_returns_k[:, :T]), None, hp,
+                                                    old_c_values=tnk(storage.c_value_preds_k[:, :T]))
+            on_tower_stream(CRITIC, lambda: (m.tower_backward(CRITIC, states[CRITIC], None, dv), reduce_async(CRITIC)))
+            on_tower_stream(COST, lambda: m.tower_backward(COST, states[COST], None, dcv))
+            join((CRITIC, COST))
+            scal = torch.cat([scal[0:4], scal_c[4:5], scal[5:]])  # [0] value-critic total, [4] cost-critic total
+        else:
+            c_adv, lam = c_adv_1, self.lagrange.lagrangian_multiplier
+            if K > 1:  # fold the K (advantage, multiplier) pairs into the one pair the fused loss takes
+                c_adv, lam = ops.combine_cost_advantages(c_adv_k.reshape(K, R), lam)
+            scal, dl, dv, _ = ops.ppo_lag_fwd_bwd(
+                outs[ACTOR]["logits"], storage.actions, storage.action_log_probs, adv_t,
+                c_adv, outs[CRITIC]["values"], storage.returns[:T], None, None,
+                lam, hp, old_values=storage.value_preds[:T])
+            with nvtx_range(f"update/rep{rep}/bwd/tower{ACTOR}"):
+                # the actor's slice crosses NVLink while the critic's backward runs
+                on_tower_stream(ACTOR, lambda: (m.tower_backward(ACTOR, states[ACTOR], dl, None), reduce_async(ACTOR)))
+            with nvtx_range(f"update/rep{rep}/bwd/tower{CRITIC}"):
+                on_tower_stream(CRITIC, lambda: m.tower_backward(CRITIC, states[CRITIC], None, dv))
+            join((ACTOR, CRITIC))
+        return scal
+
+    _RC_FIELDS = ("text_idx", "time_step", "in_hand", "traj_nt", "perm_tn", "perm_nt")
+
+    def _repeat_graphed(self, key, rc, ctx):
+        """The same repeat replayed from a CUDA graph.  First call for a key: eager (it also sets the kernels' launch
+        attributes, which cannot be captured).  Second call: the rollout context is copied into buffers that live as
+        long as the graph, the repeat is captured over them and replayed.  Later calls: refresh the buffers, replay."""
+        lib = L.load_library()
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs[key] = {"graph": None}
+            return self._repeat(rc, ctx, 0, None, overlap=True)
+        if g["graph"] is None:
+            R = rc.T * rc.N
+            st = type(rc)(rc.T, rc.N, rc.L, [v.clone() for v in rc.vis],
+                          torch.zeros(R * rc.L, rc.text_u.shape[1], device=rc.text_u.device, dtype=rc.text_u.dtype),
+                          *[(getattr(rc, f).clone() if getattr(rc, f) is not None else None) for f in self._RC_FIELDS],
+                          key=("static",) + tuple(key))
+            g["rc"], g["src_key"] = st, None
+            self._refresh_static(g, rc)
+            cap = torch.cuda.Stream(device=self.model.dev)
+            with torch.cuda.stream(cap):
+                L.get_ctx()  # the library context of the capture stream allocates its scratch: not capturable
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = lib.svla_launch_count()
+            with torch.cuda.graph(graph, stream=cap):
+                g["scal"] = self._repeat(st, ctx, 0, None, overlap=False)
+            g["launches"] = lib.svla_launch_count() - n0  # counted at capture; nothing ran yet
+            lib.svla_launch_count_add(C.c_ulonglong(-g["launches"] & 0xFFFFFFFFFFFFFFFF))
+            g["graph"] = graph
+        self._refresh_static(g, rc)
+        g["graph"].replay()
+        lib.svla_launch_count_add(g["launches"])
+        return g["scal"]
+
+    def _refresh_static(self, g, rc):
+        """New rollout -> copy its observation-derived context into the buffers the graph reads."""
+        if g["src_key"] == rc.key:
+            return
+        st = g["rc"]
+        for a, b in zip(st.vis, rc.vis):
+            a.copy_(b)
+        st.text_u[: rc.text_u.shape[0]].copy_(rc.text_u)
+        for f in self._RC_FIELDS:
+            if getattr(rc, f) is not None:
+                getattr(st, f).copy_(getattr(rc, f))
+        g["src_key"] = rc.key
 
     # ------------------------------------------------------------------ resume state
     def state_dict(self) -> Dict:

@@ -286,3 +286,44 @@ def test_updater_state_dict_resume(dev):
     named = u_b.named_optimizer_state()
     k = "critic_tsfm.decoder.norm.weight"
     assert named[k]["exp_avg"].shape == m_b.get_parameter(k).shape and named[k]["step"] == 4
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches(dev):
+    """PPOLagConfig(cuda_graphs=True): the forward + loss + backward of an update repeat is captured once and replayed
+    (what data-parallel runs use, where enqueueing ~700 launches per repeat from Python is slower than the GPU).  Two
+    whole updates on two different rollouts -- the second one only refreshes the graph's static rollout context --
+    must leave exactly the parameters, optimizer state, multiplier and loss scalars of the eagerly launched updates,
+    and the launch counter must count replayed launches."""
+    from safevla_b200 import _lib as L
+    from safevla_b200.model import B200SafeActorCritic
+    from safevla_b200.storage import B200RolloutStorage
+    from safevla_b200.updater import PPOLagConfig, PPOLagUpdater
+    T, N, A, C = 8, 4, 6, 1
+    sd = init_state_dict(A, C, seed=21, actor_gain=1.0)
+    lib = L.load_library()
+    results = {}
+    for mode in (False, True):
+        model = B200SafeActorCritic(A, C, precision="bf16", state_dict=sd, device=dev, extras="off")
+        upd = PPOLagUpdater(model, PPOLagConfig(update_repeats=3, lr=1e-3, cuda_graphs=mode))
+        st = B200RolloutStorage(T, dev)
+        scal, counts = [], []
+        for seed in (77, 78, 79):
+            ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.2, seed=seed))
+            g = torch.Generator().manual_seed(seed)
+            vp, cvp = torch.randn(T + 1, N, 1, generator=g), torch.randn(T + 1, N, 1, generator=g).abs()
+            st.load_rollout(ro, vp, cvp, -1.7 + 0.1 * torch.randn(T, N, generator=g))
+            model._ctx_cache = None
+            n0 = lib.svla_launch_count()
+            res = upd.update(st)
+            torch.cuda.synchronize()
+            counts.append(lib.svla_launch_count() - n0)
+            scal.append(res["loss_scalars"].clone())
+            st.after_updates()
+        results[mode] = (model.param_arena.clone(), upd.exp_avg.clone(), upd.lagrange.lagrangian_multiplier.clone(), scal,
+                         counts, len(upd._graphs))
+    eager, graph = results[False], results[True]
+    assert torch.equal(eager[0], graph[0]) and torch.equal(eager[1], graph[1]) and torch.equal(eager[2], graph[2])
+    for a, b in zip(eager[3], graph[3]):
+        assert torch.equal(a, b)
+    assert eager[5] == 0 and graph[5] == 1          # one graph, reused by all three updates
+    assert graph[4][1] == eager[4][1] and graph[4][2] == eager[4][2]  # replayed launches are counted
