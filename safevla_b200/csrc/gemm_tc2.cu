@@ -122,8 +122,9 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();  // CTA-local visibility of the TMEM base / barrier init (the cluster barrier below orders it too, but
-                    // compute-sanitizer's racecheck only models CTA barriers: it flagged this read without it)
+  __syncthreads();  // CTA-local ordering of the TMEM base / barrier init ahead of the cluster barrier (racecheck still
+                    // reports the pair-wide tcgen05.alloc.cta_group::2 itself: both CTAs' allocators write the base
+                    // into both CTAs' shared memory, a protocol the tool does not model; profiles/sanitizer_r02.md)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
