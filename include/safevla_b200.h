@@ -171,6 +171,8 @@ typedef struct {
   unsigned int site;        /* which dropout of the network (tower, layer, position) */
   unsigned int step;        /* update repeat / rollout counter */
   unsigned int row0;        /* global row of the tensor's first row (row chunks of one logical tensor) */
+  unsigned int row_stride;  /* global rows between consecutive rows of the tensor (0 = 1); the CLS-row tensors of the
+                               last fusion layer address every S-th row of the full sequence tensor */
 } svla_dropout;
 
 /* out[r, c] = keep(r, c) ? x[r, c] / (1 - p) : 0 over [rows, cols] (row strides ldx / ldo; in place allowed).  The
@@ -278,13 +280,15 @@ int svla_set_attn_impl(int impl);
 /* Single-query attention of the LAST fusion layer: only output token 0 of the fusion transformer is
  * consumed (allenact_dino_transformer.py:708), so its query/out-proj/FFN run for that row alone.
  * q [B, H*dh] (ldq), k/v rows b*S+s (ldkv), o [B, H*dh]; lse [B,H]. */
+/* `drop` (may be NULL): dropout on the attention probabilities of the single query row, bf16 only; mask row
+ * (b * H + h) * 128, i.e. the CLS row of the full-sequence mask the svla_attn_drop_* kernels use. */
 int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
                       void* o, long long ldo, int dtype, float* lse, int B, int S, int H, int dh, float scale,
-                      svla_stream stream);
+                      const svla_dropout* drop, svla_stream stream);
 int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, const void* k, const void* v, long long ldkv,
                       const void* o, const void* d_o, long long ldo, void* dq, long long lddq, void* dk, void* dv,
                       long long lddkv, int dtype, const float* lse, int B, int S, int H, int dh, float scale,
-                      svla_stream stream);
+                      const svla_dropout* drop, svla_stream stream);
 
 /* Single-step decoder attention against the KV cache (rollout-side T = 1 inference; llama/model.py:224-247,279-317,
  * episode-start mask allenact_dino_transformer.py:386-397).  q [N, H*dh] (ldq); cache_k / cache_v [N, cache_rows,

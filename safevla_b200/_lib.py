@@ -38,7 +38,8 @@ class AdamHparams(C.Structure):
 
 class Dropout(C.Structure):
     """svla_dropout: counter-based mask spec (p, seed, site, step, row0)."""
-    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("site", C.c_uint), ("step", C.c_uint), ("row0", C.c_uint)]
+    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("site", C.c_uint), ("step", C.c_uint), ("row0", C.c_uint),
+                ("row_stride", C.c_uint)]
 
 
 class GemmDesc(C.Structure):
@@ -93,9 +94,9 @@ PROTOTYPES: Dict[str, list] = {
                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
     "svla_set_attn_impl": [C.c_int],
     "svla_attn_cls_fwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, C.c_int, c_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                          C.c_float, c_p],
+                          C.c_float, c_p, c_p],
     "svla_attn_cls_bwd": [c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, C.c_int, c_p,
-                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p],
+                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_p, c_p],
     "svla_patchify_u8": [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int,
                          c_p],
     "svla_vit_assemble": [c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p],

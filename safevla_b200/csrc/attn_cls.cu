@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bf
                                                                 const __nv_bfloat16* __restrict__ k,
                                                                 const __nv_bfloat16* __restrict__ v, long long ldkv,
                                                                 __nv_bfloat16* __restrict__ o, long long ldo,
-                                                                float* __restrict__ lse, int B, int S, int H, float scale) {
+                                                                float* __restrict__ lse, int B, int S, int H, float scale,
+                                                                DropArgs drop) {
   const int lane = threadIdx.x & 31, r = lane >> 3, c = lane & 7;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)B * H) return;
@@ -242,8 +243,10 @@ __global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bf
     for (int i = 0; i < kBatch; ++i) {
       const int j = 4 * (i0 + i) + r;
       if (j < S) {
-        const float p = __expf(sc[i0 + i] - mx);
-        sum += p;
+        float p = __expf(sc[i0 + i] - mx);
+        sum += p;  // the normaliser is the undropped row sum
+        if (drop.thr != 0u)  // mask row = the CLS row of this (sequence, head) in the full-sequence mask
+          p = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * 128u, (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
         float vf[8];
         unpack8(vr[i], vf);
 #pragma unroll
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(128, 4) attn_cls_bwd_bf16_kernel(
     const __nv_bfloat16* __restrict__ v, long long ldkv, const __nv_bfloat16* __restrict__ o,
     const __nv_bfloat16* __restrict__ d_o, long long ldo, __nv_bfloat16* __restrict__ dq, long long lddq,
     __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, long long lddkv, const float* __restrict__ lse, int B,
-    int S, int H, float scale) {
+    int S, int H, float scale, DropArgs drop) {
   const int lane = threadIdx.x & 31, r = lane >> 3, c = lane & 7;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)B * H) return;
@@ -317,12 +320,15 @@ __global__ void __launch_bounds__(128, 4) attn_cls_bwd_bf16_kernel(
       dp = group8_sum(dp);
       if (ok) {
         const float p = __expf(s * scale - l_);
-        const float dsj = p * (dp - delta);
+        float pm = p;  // P~ = P * keep / (1 - p_drop): delta = dO . O = rowsum(P~ dP) holds with O computed from P~
+        if (drop.thr != 0u)
+          pm = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * 128u, (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
+        const float dsj = fmaf(pm, dp, -p * delta);
         float a[8], bb[8];
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
           a[d] = scale * dsj * qv[d];
-          bb[d] = p * dov[d];
+          bb[d] = pm * dov[d];
           dqa[d] = fmaf(dsj, kf[d], dqa[d]);
         }
         *reinterpret_cast<uint4*>(dkb + (long long)j * lddkv) = pack8(a);
@@ -341,8 +347,10 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, const void* k, const void* v,
                                  long long ldkv, void* o, long long ldo, int dtype, float* lse, int B, int S, int H,
-                                 int dh, float scale, svla_stream stream) {
+                                 int dh, float scale, const svla_dropout* drop, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && q && k && v && o && lse, "NULL argument");
+  SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
+  const DropArgs da = make_drop_args(drop);
   SVLA_CHECK_ARG(dh == DH && S >= 1 && S <= 32 * kMaxChunks, "head dim must be 64 and S <= 256");
   SVLA_CHECK_ARG(ldq % 4 == 0 && ldkv % 4 == 0 && ldo % 4 == 0, "leading dims must be multiples of 4");
   if (B <= 0) return SVLA_OK;
@@ -353,7 +361,7 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
 #define SVLA_CLS_FWD(NQ_)                                                                                          \
   attn_cls_fwd_bf16_kernel<NQ_><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,         \
                                                       (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, lse, B, S, \
-                                                      H, scale)
+                                                      H, scale, da)
     if (S <= 64) SVLA_CLS_FWD(16);
     else if (S <= 128) SVLA_CLS_FWD(32);
     else SVLA_CLS_FWD(64);
@@ -361,6 +369,7 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
     SVLA_LAUNCH_CHECK();
     return SVLA_OK;
   }
+  SVLA_CHECK_ARG(da.thr == 0u, "CLS-row attention with dropout: bf16, 16-byte aligned operands");
   SVLA_DISPATCH_DTYPE(dtype, T, (attn_cls_fwd_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
                                     (const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (T*)o, ldo, lse, B, S, H, scale)));
   SVLA_LAUNCH_CHECK();
@@ -370,8 +379,10 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
 extern "C" int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, const void* k, const void* v,
                                  long long ldkv, const void* o, const void* d_o, long long ldo, void* dq,
                                  long long lddq, void* dk, void* dv, long long lddkv, int dtype, const float* lse,
-                                 int B, int S, int H, int dh, float scale, svla_stream stream) {
+                                 int B, int S, int H, int dh, float scale, const svla_dropout* drop, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && q && k && v && o && d_o && dq && dk && dv && lse, "NULL argument");
+  SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
+  const DropArgs da = make_drop_args(drop);
   SVLA_CHECK_ARG(dh == DH && S >= 1 && S <= 32 * kMaxChunks, "head dim must be 64 and S <= 256");
   if (B <= 0) return SVLA_OK;
   const long long threads = (long long)B * H * 32;
@@ -380,10 +391,11 @@ extern "C" int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, co
     attn_cls_bwd_bf16_kernel<64><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (const __nv_bfloat16*)o,
         (const __nv_bfloat16*)d_o, ldo, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, lddkv, lse, B, S,
-        H, scale);
+        H, scale, da);
     SVLA_LAUNCH_CHECK();
     return SVLA_OK;
   }
+  SVLA_CHECK_ARG(da.thr == 0u, "CLS-row attention with dropout: bf16, 16-byte aligned operands");
   SVLA_DISPATCH_DTYPE(dtype, T, (attn_cls_bwd_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
                                     (const T*)q, ldq, (const T*)k, (const T*)v, ldkv, (const T*)o, (const T*)d_o, ldo,
                                     (T*)dq, lddq, (T*)dk, (T*)dv, lddkv, lse, B, S, H, scale)));

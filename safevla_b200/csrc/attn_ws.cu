@@ -73,8 +73,7 @@ struct WsArgs {
   float* lse;
   void* o; long long ldo;                  // forward output (bf16: NP = 1, fp32: NP = 3)
   void* dq; void* dk; void* dv; long long ldd;
-  DropArgs drop;        // dropout on the attention probabilities (thr == 0: off); mask row = drop_row0 + item * 128 + query
-  uint32_t drop_row0;
+  DropArgs drop;        // dropout on the attention probabilities (thr == 0: off); mask row = drop.row0 + item * 128 + query
 };
 
 // 8 consecutive P values of row i (columns c8*8 ..) into the hi (and lo) tile
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_ws_fwd_kernel(const __gri
           s4[e & 3] += p[e];
         }
         if (MODE == SVLA_ATTN_FULL && a.drop.thr != 0u) {  // normaliser = undropped row sum; P V sees the dropped row
-          const uint32_t keep = dropout_keep8(a.drop, a.drop_row0 + (uint32_t)(w * 128 + i), (uint32_t)c8);
+          const uint32_t keep = dropout_keep8(a.drop, a.drop.row0 + (uint32_t)(w * 128 + i), (uint32_t)c8);
 #pragma unroll
           for (int e = 0; e < 8; ++e) p[e] = ((keep >> e) & 1u) ? p[e] * a.drop.scale : 0.f;
         }
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
         kb[0] = kb[1] = 0u;
 #pragma unroll
         for (int l8 = 0; l8 < 8; ++l8)
-          kb[l8 >> 2] |= dropout_keep8(a.drop, a.drop_row0 + (uint32_t)(w * 128 + i), (uint32_t)(hf * 8 + l8)) << ((l8 & 3) * 8);
+          kb[l8 >> 2] |= dropout_keep8(a.drop, a.drop.row0 + (uint32_t)(w * 128 + i), (uint32_t)(hf * 8 + l8)) << ((l8 & 3) * 8);
       }
       const float dsc = (MODE == SVLA_ATTN_FULL) ? a.drop.scale : 1.f;  // 1 when dropout is off
       if (MODE == SVLA_ATTN_TRAJ_CAUSAL) {
@@ -844,7 +843,6 @@ static int attn_ws_fwd_impl(svla_ctx* ctx, int mode, const void* q, const void* 
   WsArgs a{};
   a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = lse; a.o = o; a.ldo = ldo;
   a.drop = make_drop_args(drop);
-  a.drop_row0 = drop ? drop->row0 : 0u;
   const int grid = std::min(B * H, ctx->sm_count);
   if (mode == SVLA_ATTN_FULL) return launch_fwd<SVLA_ATTN_FULL, 1>(m, a, grid, st);
   return launch_fwd<SVLA_ATTN_TRAJ_CAUSAL, 1>(m, a, grid, st);
@@ -869,7 +867,6 @@ static int attn_ws_bwd_impl(svla_ctx* ctx, int mode, const void* q, const void* 
   a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = const_cast<float*>(lse);
   a.dq = dq; a.dk = dk; a.dv = dv; a.ldd = ldd;
   a.drop = make_drop_args(drop);
-  a.drop_row0 = drop ? drop->row0 : 0u;
   const int grid = std::min(B * H, ctx->sm_count);
   if (mode == SVLA_ATTN_FULL) return launch_bwd<SVLA_ATTN_FULL>(m, a, grid, st);
   return launch_bwd<SVLA_ATTN_TRAJ_CAUSAL>(m, a, grid, st);

@@ -63,6 +63,8 @@ static inline DropArgs make_drop_args(const svla_dropout* d) {
   } else {
     a.scale = 1.f;
   }
+  a.row0 = d ? d->row0 : 0u;
+  a.row_stride = (d && d->row_stride) ? d->row_stride : 1u;
   return a;
 }
 

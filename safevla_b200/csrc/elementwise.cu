@@ -295,14 +295,13 @@ __global__ void __launch_bounds__(256) scale_by_kernel(float* __restrict__ x, lo
 // ---- stand-alone dropout ------------------------------------------------------------------------------------------
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) dropout_rows_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ out,
-                                                           long long ldo, long long rows, int cols, DropArgs d,
-                                                           uint32_t row0) {
+                                                           long long ldo, long long rows, int cols, DropArgs d) {
   const int g8 = cols >> 3;  // column groups of eight: one Philox call each
   const long long total = rows * g8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / g8;
     const int cg = (int)(i - r * g8);
-    const uint32_t keep = dropout_keep8(d, row0 + (uint32_t)r, (uint32_t)cg);
+    const uint32_t keep = dropout_keep8(d, d.row0 + (uint32_t)r * d.row_stride, (uint32_t)cg);
     const float4 a = load4<TI>(x + r * ldx + cg * 8), b = load4<TI>(x + r * ldx + cg * 8 + 4);
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     float o[8];
@@ -341,7 +340,7 @@ extern "C" int svla_dropout_rows(svla_ctx* ctx, const void* x, int dtype_x, long
   const DropArgs d = make_drop_args(drop);
   DISPATCH2E(dtype_x, TI, dtype_out, TO,
              (dropout_rows_kernel<TI, TO><<<ew_grid(ctx, rows * (cols / 8), 256), 256, 0, as_stream(stream)>>>(
-                 reinterpret_cast<const TI*>(x), ldx, reinterpret_cast<TO*>(out), ldo, rows, cols, d, drop->row0)));
+                 reinterpret_cast<const TI*>(x), ldx, reinterpret_cast<TO*>(out), ldo, rows, cols, d)));
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }

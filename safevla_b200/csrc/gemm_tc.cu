@@ -431,7 +431,6 @@ int svla_gemm_tc(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   g.aux = d->aux; g.ldaux = d->ldaux; g.dtypeAux = d->dtypeAux;
   g.epilogue = d->epilogue; g.accumulate = d->accumulate; g.alpha = d->alpha;
   g.drop = make_drop_args(d->epilogue == SVLA_EPI_RELU_BITS ? d->dropout : nullptr);
-  g.drop_row0 = (d->dropout && d->epilogue == SVLA_EPI_RELU_BITS) ? d->dropout->row0 : 0u;
   g.ws = reinterpret_cast<float*>(ctx->ws);
   g.asum = nullptr; g.asum_ws = nullptr;
   static const int dbg_env = getenv("SVLA_TC_DBG") ? atoi(getenv("SVLA_TC_DBG")) : 0;

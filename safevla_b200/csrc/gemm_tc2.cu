@@ -363,7 +363,6 @@ int svla_gemm_tc2(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
   g.aux = d->aux; g.ldaux = d->ldaux; g.dtypeAux = d->dtypeAux;
   g.epilogue = d->epilogue; g.accumulate = d->accumulate; g.alpha = d->alpha;
   g.drop = make_drop_args(d->epilogue == SVLA_EPI_RELU_BITS ? d->dropout : nullptr);
-  g.drop_row0 = (d->dropout && d->epilogue == SVLA_EPI_RELU_BITS) ? d->dropout->row0 : 0u;
   g.ws = reinterpret_cast<float*>(ctx->ws);
   g.asum = (amn && bmn) ? d->colsum_a : nullptr;
   g.asum_ws = g.ws + (size_t)g.splits * d->M * d->N;

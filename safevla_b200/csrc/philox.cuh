@@ -19,6 +19,7 @@ struct DropArgs {
   float scale;         // 1 / (1 - p)
   uint32_t key0, key1; // seed
   uint32_t site, step;
+  uint32_t row0, row_stride;  // global row of local row r: row0 + r * row_stride
 };
 
 __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {

@@ -109,7 +109,6 @@ struct TcArgs {
   float* asum_ws;  // its split-K partials
   int tma_store;
   DropArgs drop;      // RELU_BITS: dropout after the ReLU (thr == 0: off)
-  uint32_t drop_row0;
   int dbg;  // SVLA_TC_DBG experiments: 1 = skip the epilogue entirely, 2 = TMEM loads only (no global stores),
             // 9 = 32-column chunks instead of the 64-column block epilogue (A/B switch used for the same-box comparison)
 };
@@ -493,7 +492,8 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
       }
       if (EPI == SVLA_EPI_RELU_BITS && g.drop.thr != 0u) {
         // FFN dropout of the encoder layer: slot j holds columns n0 + 8 j .. + 8 of this lane's row = one Philox group
-        const uint32_t keep = dropout_keep8(g.drop, g.drop_row0 + (uint32_t)(m0 + lane), (uint32_t)((n0 >> 3) + j));
+        const uint32_t keep = dropout_keep8(g.drop, g.drop.row0 + (uint32_t)(m0 + lane) * g.drop.row_stride,
+                                            (uint32_t)((n0 >> 3) + j));
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           uint32_t& w = *reinterpret_cast<uint32_t*>(&h[e]);

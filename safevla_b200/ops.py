@@ -169,10 +169,10 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 
 # ---- dropout -----------------------------------------------------------------------------------
-def dropout_spec(p: float, seed: int, site: int, step: int, row0: int = 0) -> L.Dropout:
-    """svla_dropout: the mask of a site is a pure function of (seed, step, site, row0 + row, column)."""
+def dropout_spec(p: float, seed: int, site: int, step: int, row0: int = 0, row_stride: int = 1) -> L.Dropout:
+    """svla_dropout: the mask of a site is a pure function of (seed, step, site, row0 + row * row_stride, column)."""
     return L.Dropout(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site) & 0xFFFFFFFF, int(step) & 0xFFFFFFFF,
-                     int(row0) & 0xFFFFFFFF)
+                     int(row0) & 0xFFFFFFFF, int(row_stride) & 0xFFFFFFFF)
 
 
 def dropout_rows(x: torch.Tensor, out: torch.Tensor, drop: L.Dropout, rows=None):
@@ -429,18 +429,20 @@ def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.1
                              scale, stream_ptr()), "svla_attn_bwd"))
 
 
-def attn_cls_fwd(q0, k, v, o, lse, B, S, H=8, dh=64, scale=0.125):
+def attn_cls_fwd(q0, k, v, o, lse, B, S, H=8, dh=64, scale=0.125, drop=None):
     assert k.stride(0) == v.stride(0)
+    dp = C.cast(C.pointer(drop), C.c_void_p) if drop is not None else None
     check(_lib().svla_attn_cls_fwd(get_ctx(), ptr(q0), q0.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), o.stride(0),
-                                   dt(q0), ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_fwd")
+                                   dt(q0), ptr(lse), B, S, H, dh, scale, dp, stream_ptr()), "svla_attn_cls_fwd")
     return o
 
 
-def attn_cls_bwd(q0, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125):
+def attn_cls_bwd(q0, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.125, drop=None):
     assert k.stride(0) == v.stride(0) and dk.stride(0) == dv.stride(0) and o.stride(0) == d_o.stride(0)
+    dp = C.cast(C.pointer(drop), C.c_void_p) if drop is not None else None
     check(_lib().svla_attn_cls_bwd(get_ctx(), ptr(q0), q0.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), ptr(d_o),
                                    o.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), dt(q0),
-                                   ptr(lse), B, S, H, dh, scale, stream_ptr()), "svla_attn_cls_bwd")
+                                   ptr(lse), B, S, H, dh, scale, dp, stream_ptr()), "svla_attn_cls_bwd")
 
 
 def patchify_u8(img, out, patch, crop_left, crop_right, mean, std):

@@ -84,9 +84,11 @@ class Tower:
         # 3 (or 6) split-bf16 products in one tcgen05 launch (ops.gemm split=); 0 = operands as they are
         self.split = split
 
-    def _site(self, layer: int, kind: int, row0: int):
-        """Dropout spec of site (tower, layer, kind): kind 0 attention probabilities, 1 dropout1, 2 FFN, 3 dropout2."""
-        return ops.dropout_spec(self.drop_p, self.drop_seed, self.tower_idx * 64 + layer * 8 + kind, self.drop_step, row0)
+    def _site(self, layer: int, kind: int, row0: int, row_stride: int = 1):
+        """Dropout spec of site (tower, layer, kind): kind 0 attention probabilities, 1 dropout1, 2 FFN, 3 dropout2.
+        Buffer row r uses mask row row0 + r * row_stride (the CLS-only last layer addresses the full-sequence mask)."""
+        return ops.dropout_spec(self.drop_p, self.drop_seed, self.tower_idx * 64 + layer * 8 + kind, self.drop_step, row0,
+                                row_stride)
 
     def _gemm(self, a, b, out, **kw):
         if self.split:
@@ -111,8 +113,9 @@ class Tower:
         `out` (those K = 512 launches are HBM-bound); bits is None where the plain ReLU epilogue ran."""
         M, N = x.shape[0], out.shape[1]
         bits_ok = x.dtype == torch.bfloat16 and M >= 256 and N % 64 == 0 and N >= 256
-        if dropout is not None and not bits_ok:
-            raise NotImplementedError("fused FFN dropout needs the bf16 tensor-core path (>= 256 token rows per chunk)")
+        if dropout is not None and not bits_ok:  # small chunks: ReLU launch, then the mask as a row pass
+            out, _ = self._lin_fwd(x, wname, bname, out, wshape=wshape, epi=EPI_RELU), None
+            return ops.dropout_rows(out, out, dropout), None
         if (keep or dropout is not None) and bits_ok:
             bits = torch.empty(M, N // 32, device=self.dev, dtype=torch.int32)
             w = self.W.w(wname, wshape, 1, dtype=x.dtype)
@@ -138,7 +141,7 @@ class Tower:
                 self._gemm(dy, w, dx, trans_b=False, aux=bits, epilogue=EPI_MASK_BITS, alpha=alpha)
             else:
                 self._gemm(dy, w, dx, trans_b=False, aux=aux, epilogue=EPI_RELU_MASK if aux is not None else EPI_NONE,
-                           residual=residual)
+                           residual=residual, alpha=alpha)
         return dx
 
     # ------------------------------------------------------------------ encoder
@@ -182,7 +185,7 @@ class Tower:
         Ms = Rc * S
         for l in range(3):
             p = ve + f"fusion_xformer.layers.{l}."
-            last = (l == 2) and self.cls_only and not dp  # with dropout every layer runs in full
+            last = (l == 2) and self.cls_only
             if not last:
                 qkv = self._lin_fwd(x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", self._new(Ms, 3 * D))
                 ao, lse = self._new(Ms, D), self._new(Rc * H * S, dtype=torch.float32)
@@ -228,21 +231,41 @@ class Tower:
                 xc = x.view(Rc, S * D)[:, :D]  # CLS rows, leading dimension S*D
                 q0 = self._gemm(xc, wi[0:D], self._new(Rc, D), trans_b=True, bias=bi[0:D])
                 ao, lse = self._new(Rc, D), self._new(Rc * H, dtype=torch.float32)
-                ops.attn_cls_fwd(q0, kv[:, 0:D], kv[:, D:2 * D], ao, lse, Rc, S, scale=1.0 / math.sqrt(DH))
-                s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Rc, D),
-                                   residual=xc)
                 m1, r1 = self._new(Rc, dtype=torch.float32), self._new(Rc, dtype=torch.float32)
-                x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Rc, D),
-                                       eps=LN_EPS, mean=m1, rstd=r1)
-                hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Rc, FF), keep=keep)
-                s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Rc, D), residual=x1)
                 m2, r2 = self._new(Rc, dtype=torch.float32), self._new(Rc, dtype=torch.float32)
-                x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Rc, D),
-                                       eps=LN_EPS, mean=m2, rstd=r2)
+                if not dp:
+                    ops.attn_cls_fwd(q0, kv[:, 0:D], kv[:, D:2 * D], ao, lse, Rc, S, scale=1.0 / math.sqrt(DH))
+                    s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
+                                       self._new(Rc, D), residual=xc)
+                    x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Rc, D),
+                                           eps=LN_EPS, mean=m1, rstd=r1)
+                    hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Rc, FF), keep=keep)
+                    s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Rc, D), residual=x1)
+                    x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Rc, D),
+                                           eps=LN_EPS, mean=m2, rstd=r2)
+                else:
+                    # the masks are those of the full layer's CLS rows: row (row_off + r) * S of each [rows * S] site
+                    crow = lambda kind: self._site(l, kind, row_off * S, S)
+                    xcc = self._new(Rc, D)  # contiguous CLS rows: the LayerNorm residual operand has no row stride
+                    ops.copy_rows(x, xcc, Rc, D, smap=RowMap(1, S, 0))
+                    ops.attn_cls_fwd(q0, kv[:, 0:D], kv[:, D:2 * D], ao, lse, Rc, S, scale=1.0 / math.sqrt(DH),
+                                     drop=self._site(l, 0, row_off * H * 128))
+                    s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Rc, D))
+                    ops.dropout_rows(s1, s1, crow(1))
+                    x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Rc, D),
+                                           res=xcc, eps=LN_EPS, mean=m1, rstd=r1)
+                    hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Rc, FF), keep=keep,
+                                             dropout=crow(2))
+                    s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Rc, D))
+                    ops.dropout_rows(s2, s2, crow(3))
+                    x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Rc, D),
+                                           res=x1, eps=LN_EPS, mean=m2, rstd=r2)
                 if keep:
                     st.t.update({f"x_{l}": x, f"kv_{l}": kv, f"q0_{l}": q0, f"ao_{l}": ao, f"lse_{l}": lse,
                                  f"s1_{l}": s1, f"m1_{l}": m1, f"r1_{l}": r1, f"x1_{l}": x1, f"hf_{l}": hf,
                                  f"s2_{l}": s2, f"m2_{l}": m2, f"r2_{l}": r2, f"hfb_{l}": hfb})
+                    if dp:
+                        st.t[f"xc_{l}"] = xcc
                 return x2, (st if keep else None)
         cls = self._new(Rc, D)
         ops.copy_rows(x, cls, Rc, D, smap=RowMap(1, S, 0))
@@ -261,7 +284,10 @@ class Tower:
         dx = None  # gradient wrt the current layer's output [Ms, D]
         for l in (2, 1, 0):
             p = ve + f"fusion_xformer.layers.{l}."
-            last = (l == 2) and self.cls_only and not dp
+            last = (l == 2) and self.cls_only
+            # mask rows of this layer's [rows, *] buffers: every sequence row, or the CLS row of each sequence
+            site = (lambda kind: self._site(l, kind, row_off * S, S)) if last else \
+                   (lambda kind: self._site(l, kind, row_off * S))
             if last:
                 rows = Rc
                 dy = d_cls
@@ -275,7 +301,7 @@ class Tower:
                                     t[f"r2_{l}"], self._new(rows, D), W.g(p + "norm2.weight"), W.g(p + "norm2.bias"),
                                     res=t[f"x1_{l}"] if dp else None)
             # gradient of the (dropped) sub-layer output: the residual branch keeps ds2, the FFN branch sees the mask
-            dy2 = ops.dropout_rows(ds2, self._new(rows, D), self._site(l, 3, row_off * S)) if dp else ds2
+            dy2 = ops.dropout_rows(ds2, self._new(rows, D), site(3)) if dp else ds2
             dhf = self._lin_bwd(dy2, t[f"hf_{l}"], p + "linear2.weight", p + "linear2.bias", dx=self._new(rows, FF),
                                 aux=t[f"hf_{l}"], bits=t.get(f"hfb_{l}"), alpha=dsc)
             del dy2
@@ -284,9 +310,9 @@ class Tower:
             del dhf, ds2
             ds1 = ops.layernorm_bwd(dx1, t[f"s1_{l}"], W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), t[f"m1_{l}"],
                                     t[f"r1_{l}"], self._new(rows, D), W.g(p + "norm1.weight"), W.g(p + "norm1.bias"),
-                                    res=t[f"x_{l}"] if dp else None)
+                                    res=(t[f"xc_{l}"] if last else t[f"x_{l}"]) if dp else None)
             del dx1
-            dy1 = ops.dropout_rows(ds1, self._new(rows, D), self._site(l, 1, row_off * S)) if dp else ds1
+            dy1 = ops.dropout_rows(ds1, self._new(rows, D), site(1)) if dp else ds1
             dao = self._lin_bwd(dy1, t[f"ao_{l}"], p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
                                 dx=self._new(rows, D))
             del dy1
@@ -297,7 +323,8 @@ class Tower:
                 kv, q0 = t[f"kv_{l}"], t[f"q0_{l}"]
                 dq0, dkv = self._new(Rc, D), self._new(Ms, 2 * D)
                 ops.attn_cls_bwd(q0, kv[:, 0:D], kv[:, D:2 * D], t[f"ao_{l}"], dao, dq0, dkv[:, 0:D], dkv[:, D:2 * D],
-                                 t[f"lse_{l}"], Rc, S, scale=1.0 / math.sqrt(DH))
+                                 t[f"lse_{l}"], Rc, S, scale=1.0 / math.sqrt(DH),
+                                 drop=self._site(l, 0, row_off * H * 128) if dp else None)
                 xc = x.view(Rc, S * D)[:, :D]
                 # K/V projections of every token
                 self._gemm(dkv, x, gwi[D:3 * D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[D:3 * D])

@@ -259,6 +259,35 @@ def test_dropout_zero_is_the_parity_path_and_modes(dev):
         B200SafeActorCritic(A, C, precision="fp32", state_dict=sd, device=dev, dropout=0.1)
 
 
+@pytest.mark.parametrize("T,N", [(6, 2), (32, 8)])
+def test_cls_only_last_layer_under_dropout_equals_the_full_layer(dev, T, N):
+    """The CLS-row shortcut of the last fusion layer (K/V for every token, everything else for row 0) addresses the
+    full layer's masks (attention row h*128 of each sequence, sub-layer rows r*S): same outputs and gradients as
+    running the full layer with the same seed.  (32, 8): 256 CLS rows, the fused bit-record FFN path; (6, 2): the
+    small-chunk fallback (ReLU launch + row pass)."""
+    from safevla_b200.model import B200SafeActorCritic
+    A, C = 6, 1
+    sd = init_state_dict(A, C, seed=17, actor_gain=1.0)
+    ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.1, seed=3))
+    obs = {k: v[:-1].to(dev) for k, v in ro["observations"].items()}
+    prev, masks = prev_actions_from(ro["actions"]).to(dev), ro["masks"][:-1].to(dev)
+    res = []
+    for cls_only in (True, False):
+        m = B200SafeActorCritic(A, C, precision="bf16", state_dict=sd, device=dev, dropout=0.1, dropout_seed=5,
+                                extras="off", cls_only_last_layer=cls_only)
+        m.set_trainable_towers((0, 1))
+        out, _ = m(obs, None, prev, masks)
+        g = torch.Generator().manual_seed(2)
+        w = torch.randn(T, N, A, generator=g).to(dev)
+        ((out.distributions.raw_logits * w).sum() + out.values.sum() * 0.3).backward()
+        res.append((out.distributions.raw_logits.detach().clone(), out.values.detach().clone(), m.grad_arena.clone()))
+    (l1, v1, g1), (l0, v0, g0) = res
+    assert (l1 - l0).abs().max().item() < 2e-2 * max(l0.abs().max().item(), 0.25)
+    assert (v1 - v0).abs().max().item() < 2e-2 * max(v0.abs().max().item(), 0.25)
+    cos = (g1.double() @ g0.double() / (g1.double().norm() * g0.double().norm())).item()
+    assert cos > 0.995 and abs(g1.norm().item() / g0.norm().item() - 1) < 1e-2, (cos, g1.norm().item(), g0.norm().item())
+
+
 def test_update_with_dropout_is_deterministic_given_the_seed(dev):
     from safevla_b200.model import B200SafeActorCritic
     from safevla_b200.storage import B200RolloutStorage
