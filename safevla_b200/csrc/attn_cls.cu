@@ -186,7 +186,7 @@ __device__ __forceinline__ float rows4_sum(float v) {
   return v;
 }
 
-template <int NQ>  // key quads: S <= 4 * NQ
+template <int NQ, bool DROP>  // key quads: S <= 4 * NQ; DROP: dropout on the probabilities (S <= 128 only)
 __global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
                                                                 const __nv_bfloat16* __restrict__ k,
                                                                 const __nv_bfloat16* __restrict__ v, long long ldkv,
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bf
       if (j < S) {
         float p = __expf(sc[i0 + i] - mx);
         sum += p;  // the normaliser is the undropped row sum
-        if (drop.thr != 0u)  // mask row = the CLS row of this (sequence, head) in the full-sequence mask
+        if (DROP)  // mask row = the CLS row of this (sequence, head) in the full-sequence mask
           p = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * 128u, (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
         float vf[8];
         unpack8(vr[i], vf);
@@ -358,13 +358,17 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
   if (dtype == SVLA_BF16 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) && al16(v) && al16(o)) {
     const unsigned grid = (unsigned)((threads + 127) / 128);
     const auto st = as_stream(stream);
-#define SVLA_CLS_FWD(NQ_)                                                                                          \
-  attn_cls_fwd_bf16_kernel<NQ_><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,         \
-                                                      (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, lse, B, S, \
-                                                      H, scale, da)
-    if (S <= 64) SVLA_CLS_FWD(16);
-    else if (S <= 128) SVLA_CLS_FWD(32);
-    else SVLA_CLS_FWD(64);
+#define SVLA_CLS_FWD(NQ_, DR_)                                                                                      \
+  attn_cls_fwd_bf16_kernel<NQ_, DR_><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,    \
+                                                           (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, lse, \
+                                                           B, S, H, scale, da)
+    SVLA_CHECK_ARG(da.thr == 0u || S <= 128, "CLS-row attention with dropout: S <= 128 (the mask rows are 128 wide)");
+    if (da.thr != 0u) {
+      if (S <= 64) SVLA_CLS_FWD(16, true);
+      else SVLA_CLS_FWD(32, true);
+    } else if (S <= 64) SVLA_CLS_FWD(16, false);
+    else if (S <= 128) SVLA_CLS_FWD(32, false);
+    else SVLA_CLS_FWD(64, false);
 #undef SVLA_CLS_FWD
     SVLA_LAUNCH_CHECK();
     return SVLA_OK;
@@ -388,6 +392,7 @@ extern "C" int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, co
   const long long threads = (long long)B * H * 32;
   if (dtype == SVLA_BF16 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 && lddkv % 8 == 0 && al16(q) &&
       al16(k) && al16(v) && al16(o) && al16(d_o) && al16(dq) && al16(dk) && al16(dv)) {
+    SVLA_CHECK_ARG(da.thr == 0u || S <= 128, "CLS-row attention with dropout: S <= 128 (the mask rows are 128 wide)");
     attn_cls_bwd_bf16_kernel<64><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (const __nv_bfloat16*)o,
         (const __nv_bfloat16*)d_o, ldo, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, lddkv, lse, B, S,

@@ -166,6 +166,7 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int cb = half * (BN / 2), ce = cb + BN / 2;
     SidePre pre;
     pre.valid = 0;
+    pre.mb = make_uint4(0u, 0u, 0u, 0u);
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tn = w % g.tiles_n, tm = (w / g.tiles_n) % g.tiles_m, sp = w / (g.tiles_n * g.tiles_m);
       const int m = tm * BM + q * 32 + lane;
@@ -173,6 +174,8 @@ svla_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int wn = w + gridDim.x;  // the tile this warp drains next: its side operand is requested early
       const int next_m0 = wn < total_work ? ((wn / g.tiles_n) % g.tiles_m) * BM + q * 32 : -1;
       const int next_nt0 = (wn % g.tiles_n) * BN;
+      bias_prefetch(pre, g, tn * BN + cb, lane, (ce - cb) / 32);
+      bits_prefetch(pre, g, tm * BM + q * 32, tn * BN + cb, lane, ce - cb);
       if (staged && g.dbg == 0) side_prefetch_first(pre, g, tm * BM + q * 32, tn * BN + cb, lane, (ce - cb) / 32);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();

@@ -225,6 +225,7 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const int cb = half * (BN2 / 2), ce = cb + BN2 / 2;
     SidePre pre;
     pre.valid = 0;
+    pre.mb = make_uint4(0u, 0u, 0u, 0u);
     for (int w = cluster_id; w < total_work; w += num_clusters) {
       const int tn = w % g.tiles_n, tm2 = (w / g.tiles_n) % tiles_m2, sp = w / (g.tiles_n * tiles_m2);
       const int m0 = tm2 * 256 + (int)rank * BM + q * 32;
@@ -233,6 +234,8 @@ svla_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const int wn = w + num_clusters;  // the tile this warp drains next: its side operand is requested early
       const int next_m0 = wn < total_work ? ((wn / g.tiles_n) % tiles_m2) * 256 + (int)rank * BM + q * 32 : -1;
       const int next_nt0 = (wn % g.tiles_n) * BN2;
+      bias_prefetch(pre, g, tn * BN2 + cb, lane, 4);
+      bits_prefetch(pre, g, m0, tn * BN2 + cb, lane, ce - cb);
       if (staged) side_prefetch_first(pre, g, m0, tn * BN2 + cb, lane, 4);  // in flight while the MMAs finish
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();

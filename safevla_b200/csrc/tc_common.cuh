@@ -222,6 +222,8 @@ __device__ __forceinline__ void piece_load(uint32_t stg_s, int lane, int j, floa
 struct SidePre {
   uint4 v[4][4];  // [chunk][piece]: this lane's 16-byte pieces of the four 32-column chunks of the next tile
   int valid;      // bit c: chunk c is in registers
+  float bias[4];  // bias of column (chunk c, lane) of the CURRENT tile (bias_prefetch)
+  uint4 mb;       // MASK_BITS: the bit record of this lane's row over the warp's 128 columns (bits_prefetch)
 };
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -246,6 +248,27 @@ __device__ __forceinline__ void side_commit(uint32_t stg_s, const uint4* v, int 
 #pragma unroll
   for (int p = 0; p < 4; ++p) sts128(stg_s + stg_off<false>(p * 8 + (lane >> 2), lane & 3), v[p]);
   __syncwarp();
+}
+// The bias of the warp's columns, requested BEFORE the wait for the accumulator: with ~228 KB of shared memory carved
+// out, L1 keeps almost nothing, so a per-chunk load next to its use is an L2 round trip on the critical path of every
+// chunk (ncu source view of the K = 512 out-projection: 18 % of all stall samples sat on the bias broadcast shuffle).
+__device__ __forceinline__ void bias_prefetch(SidePre& pre, const TcArgs& g, int n0, int lane, int nch) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    pre.bias[c] = (g.bias != nullptr && g.splits == 1 && c < nch && n0 + c * 32 < g.N) ? __ldg(g.bias + n0 + c * 32 + lane) : 0.f;
+}
+// Bit records (RELU_BITS / MASK_BITS) of a warp that drains 128 columns are moved as ONE 16-byte access per row and tile
+// -- the record of a 256-column tile is 32 bytes, one sector -- instead of one 8-byte access per 64-column block.
+__device__ __forceinline__ bool bits_wide(const TcArgs& g, int n_begin, int ncols) {
+  return ncols == 128 && n_begin + 128 <= g.N && (g.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0;
+}
+// the mask record of the backward launch does not depend on the accumulator either: requested before the wait
+__device__ __forceinline__ void bits_prefetch(SidePre& pre, const TcArgs& g, int m0, int n_begin, int lane, int ncols) {
+  if (g.epilogue != SVLA_EPI_MASK_BITS || g.splits > 1 || !bits_wide(g, n_begin, ncols)) return;
+  pre.mb = make_uint4(0u, 0u, 0u, 0u);
+  if (m0 + lane < g.M)
+    pre.mb = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(g.aux) + (long long)(m0 + lane) * g.ldaux +
+                                                  (n_begin >> 5)));
 }
 // every chunk of a warp's first tile, issued by the caller BEFORE it waits for the accumulator
 __device__ __forceinline__ void side_prefetch_first(SidePre& pre, const TcArgs& g, int m0, int n0, int lane, int nch) {
@@ -324,9 +347,8 @@ __device__ __forceinline__ void epilogue_staged_impl(const TcArgs& g, const CUte
       }
     }
     // bias of the 32 columns: one coalesced load (lane l holds column l), broadcast by shuffles after the wait --
-    // holding all 32 values per lane costs 31 more registers than the kernel has
-    float bias_l = 0.f;
-    if (!part && has_bias) bias_l = __ldg(g.bias + n0 + lane);
+    // holding all 32 values per lane costs 31 more registers than the kernel has.  Loaded by bias_prefetch.
+    const float bias_l = pre.bias[chunk];
     tmem_wait_ld();
     // which ops can run on the packed bf16 pairs after the conversion
     const bool relu_packed = !F32 && !part && epi == SVLA_EPI_RELU && !has_res && !has_acc;
@@ -429,10 +451,13 @@ __device__ __forceinline__ void epilogue_staged_impl(const TcArgs& g, const CUte
 // The per-chunk fixed costs (store-buffer wait, warp syncs, the proxy fence with its MEMBAR, the TMA issue) are paid
 // once per 64 columns instead of once per 32: two LDTMs are in flight together, the 32 x 128 B staging tile (128B
 // swizzle, the warp's whole 4 KB) leaves through ONE TMA store of full 128-byte row segments.
-template <int EPI, bool BIAS>
+template <int EPI, bool BIAS, bool DROP = false>
 __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensorMap* mapC2, uint8_t* stg0, uint32_t taddr,
-                                                 int m0, int ntile0, int c_begin, int c_end, int lane) {
+                                                 int m0, int ntile0, int c_begin, int c_end, int lane, const SidePre& pre) {
   const uint32_t stg_s = smem_u32(stg0);
+  constexpr bool kBits = EPI == SVLA_EPI_RELU_BITS || EPI == SVLA_EPI_MASK_BITS;
+  const bool wide = kBits && bits_wide(g, ntile0 + c_begin, c_end - c_begin);
+  uint4 rec = (EPI == SVLA_EPI_MASK_BITS) ? pre.mb : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
   for (int cb = c_begin; cb < c_end; cb += 64) {
     const int n0 = ntile0 + cb;
@@ -440,16 +465,17 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
     uint32_t r0[32], r1[32];
     tmem_ld32(taddr + cb, r0);
     tmem_ld32(taddr + cb + 32, r1);
-    float b0 = 0.f, b1 = 0.f;
-    if (BIAS) {
-      b0 = __ldg(g.bias + n0 + lane);
-      b1 = __ldg(g.bias + n0 + 32 + lane);
-    }
+    const bool second = cb != c_begin;  // a warp drains one or two 64-column blocks per tile
+    const float b0 = BIAS ? (second ? pre.bias[2] : pre.bias[0]) : 0.f;
+    const float b1 = BIAS ? (second ? pre.bias[3] : pre.bias[1]) : 0.f;
     // bit record of this lane's row: two words (columns n0 .. n0 + 31, n0 + 32 .. n0 + 63)
     uint32_t* bits_p = reinterpret_cast<uint32_t*>(const_cast<void*>(g.aux)) + (long long)(m0 + lane) * g.ldaux + (n0 >> 5);
     uint2 mb = make_uint2(0u, 0u);
     uint32_t mbp0[4] = {0u, 0u, 0u, 0u}, mbp1[4] = {0u, 0u, 0u, 0u};
-    if (EPI == SVLA_EPI_MASK_BITS && m0 + lane < g.M) mb = __ldg(reinterpret_cast<const uint2*>(bits_p));
+    if (EPI == SVLA_EPI_MASK_BITS) {
+      if (wide) mb = second ? make_uint2(rec.z, rec.w) : make_uint2(rec.x, rec.y);
+      else if (m0 + lane < g.M) mb = __ldg(reinterpret_cast<const uint2*>(bits_p));
+    }
     tmem_wait_ld();
     if (g.alpha != 1.f) {
 #pragma unroll
@@ -481,16 +507,22 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
       const int jj = j & 3;
       uint4 u;
       __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-      const float dsc = (EPI == SVLA_EPI_RELU_BITS) ? g.drop.scale : 1.f;  // 1 / (1 - p) of the fused dropout (fp32)
+      if (DROP) {
+        const float dsc = g.drop.scale;  // 1 / (1 - p) of the fused dropout, applied in fp32
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]) * dsc, __uint_as_float(r[jj * 8 + 2 * e + 1]) * dsc);
+        for (int e = 0; e < 4; ++e)
+          h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]) * dsc, __uint_as_float(r[jj * 8 + 2 * e + 1]) * dsc);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          h[e] = __floats2bfloat162_rn(__uint_as_float(r[jj * 8 + 2 * e]), __uint_as_float(r[jj * 8 + 2 * e + 1]));
+      }
       if (EPI == SVLA_EPI_RELU || EPI == SVLA_EPI_RELU_BITS) {
         const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], z);
       }
-      if (EPI == SVLA_EPI_RELU_BITS && g.drop.thr != 0u) {
+      if (EPI == SVLA_EPI_RELU_BITS && DROP) {
         // FFN dropout of the encoder layer: slot j holds columns n0 + 8 j .. + 8 of this lane's row = one Philox group
         const uint32_t keep = dropout_keep8(g.drop, g.drop.row0 + (uint32_t)(m0 + lane) * g.drop.row_stride,
                                             (uint32_t)((n0 >> 3) + j));
@@ -527,9 +559,17 @@ __device__ __forceinline__ void epilogue_block64(const TcArgs& g, const CUtensor
       }
       sts128(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), u);
     }
-    if (EPI == SVLA_EPI_RELU_BITS && m0 + lane < g.M && g.dbg != 8)
-      *reinterpret_cast<uint2*>(bits_p) = make_uint2((mbp0[0] | mbp0[1]) | (mbp0[2] | mbp0[3]),
-                                                     (mbp1[0] | mbp1[1]) | (mbp1[2] | mbp1[3]));
+    if (EPI == SVLA_EPI_RELU_BITS && g.dbg != 8) {
+      const uint32_t w0 = (mbp0[0] | mbp0[1]) | (mbp0[2] | mbp0[3]), w1 = (mbp1[0] | mbp1[1]) | (mbp1[2] | mbp1[3]);
+      if (!wide) {
+        if (m0 + lane < g.M) *reinterpret_cast<uint2*>(bits_p) = make_uint2(w0, w1);
+      } else if (!second) {
+        rec.x = w0; rec.y = w1;
+      } else {  // both blocks of the warp's 128 columns: one 16-byte store
+        rec.z = w0; rec.w = w1;
+        if (m0 + lane < g.M) *reinterpret_cast<uint4*>(bits_p - 2) = rec;
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
@@ -558,14 +598,18 @@ __device__ __forceinline__ void epilogue_staged_t(const TcArgs& g, const CUtenso
     else SVLA_EPI_CALL(-1, false, false, false);
   } else {
     const bool blk = g.tma_store && !rs && !ac && e != SVLA_EPI_RELU_MASK && g.dbg != 9;  // 64-column blocks
-    if (e == SVLA_EPI_RELU_BITS && b) epilogue_block64<SVLA_EPI_RELU_BITS, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
-    else if (e == SVLA_EPI_RELU_BITS) epilogue_block64<SVLA_EPI_RELU_BITS, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
-    else if (e == SVLA_EPI_MASK_BITS) epilogue_block64<SVLA_EPI_MASK_BITS, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    if (e == SVLA_EPI_RELU_BITS && g.drop.thr != 0u) {
+      if (b) epilogue_block64<SVLA_EPI_RELU_BITS, true, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+      else epilogue_block64<SVLA_EPI_RELU_BITS, false, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+    }
+    else if (e == SVLA_EPI_RELU_BITS && b) epilogue_block64<SVLA_EPI_RELU_BITS, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+    else if (e == SVLA_EPI_RELU_BITS) epilogue_block64<SVLA_EPI_RELU_BITS, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+    else if (e == SVLA_EPI_MASK_BITS) epilogue_block64<SVLA_EPI_MASK_BITS, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
     else if (ac) SVLA_EPI_CALL(-1, false, false, false);
-    else if (blk && e == SVLA_EPI_NONE && b) epilogue_block64<SVLA_EPI_NONE, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
-    else if (blk && e == SVLA_EPI_NONE && !b) epilogue_block64<SVLA_EPI_NONE, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
-    else if (blk && e == SVLA_EPI_RELU && b) epilogue_block64<SVLA_EPI_RELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
-    else if (blk && e == SVLA_EPI_GELU && b) epilogue_block64<SVLA_EPI_GELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane);
+    else if (blk && e == SVLA_EPI_NONE && b) epilogue_block64<SVLA_EPI_NONE, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+    else if (blk && e == SVLA_EPI_NONE && !b) epilogue_block64<SVLA_EPI_NONE, false>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+    else if (blk && e == SVLA_EPI_RELU && b) epilogue_block64<SVLA_EPI_RELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
+    else if (blk && e == SVLA_EPI_GELU && b) epilogue_block64<SVLA_EPI_GELU, true>(g, mapC2, stg0, taddr, m0, ntile0, c_begin, c_end, lane, pre);
     else if (e == SVLA_EPI_NONE && b && !rs) SVLA_EPI_CALL(SVLA_EPI_NONE, true, false, false);
     else if (e == SVLA_EPI_RELU && b && !rs) SVLA_EPI_CALL(SVLA_EPI_RELU, true, false, false);
     else if (e == SVLA_EPI_NONE && b && rs) SVLA_EPI_CALL(SVLA_EPI_NONE, true, true, false);
