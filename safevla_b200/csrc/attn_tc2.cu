@@ -298,8 +298,8 @@ attn_tc2_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
               p[e] = ok ? exp2f(__uint_as_float(rs[j8 * 8 + e]) * sl2 - l2) : 0.f;
               ds[e] = ok ? p[e] * (__uint_as_float(rp[j8 * 8 + e]) - dl) : 0.f;
             }
-            store_p8(sP, qrow, (cb >> 3) + j8, p);
-            store_p8(sdS, qrow, (cb >> 3) + j8, ds);
+            store_p8_sts(sP, qrow, (cb >> 3) + j8, p);
+            store_p8_sts(sdS, qrow, (cb >> 3) + j8, ds);
           }
         }
         fence_async_smem();

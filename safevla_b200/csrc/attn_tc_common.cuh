@@ -37,6 +37,16 @@ __device__ __forceinline__ void store_p8(uint8_t* base, int i, int c8, const flo
   const int chunk = c8 >> 3, cc = c8 & 7;
   *reinterpret_cast<uint4*>(base + chunk * 16384 + i * 128 + ((cc ^ (i & 7)) << 4)) = u;
 }
+// the same through an explicit st.shared (the backward kernels: measured faster there, slower in the forward ones,
+// where the volatile asm keeps the compiler from interleaving the stores with the exponentials)
+__device__ __forceinline__ void store_p8_sts(uint8_t* base, int i, int c8, const float* v) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  const int chunk = c8 >> 3, cc = c8 & 7;
+  sts128(smem_u32(base) + chunk * 16384 + i * 128 + ((cc ^ (i & 7)) << 4), u);
+}
 
 struct AttnTcArgs {
   int mode, B, S, H;

@@ -58,6 +58,14 @@ __device__ __forceinline__ float ex2_approx(float x) {  // 2^x (ex2.approx.ftz: 
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -416,12 +424,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
     const int hf = (warp - 4) >> 2;  // column half [64 hf, 64 hf + 64)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sl2 = a.scale * kLog2e;
+    // the row's log-sum-exp is requested one item ahead: loaded next to its use it put an L2 / DRAM round trip in
+    // front of every item (the accumulators are usually ready when this group gets to them)
+    float lse_next = (n_items > 0 && i < S) ? a.lse[(long long)blockIdx.x * S + i] : 0.f;  // item w: rows w * S ..
     for (int it = 0; it < n_items; ++it) {
       const int w = blockIdx.x + it * gridDim.x, b = w / H, h = w % H, t = it & 1;
       const long long row0 = (long long)b * S;
       const int* traj = sTraj + t * 128;
       if (MODE == SVLA_ATTN_TRAJ_CAUSAL && hf == 0) sTraj[t * 128 + i] = (i < S) ? (int)a.traj[row0 + i] : -1 - i;
-      const float lse2 = (i < S) ? a.lse[((long long)b * H + h) * S + i] * kLog2e : 0.f;
+      const float lse2 = lse_next * kLog2e;
       mbar_wait(&sdp_full[t], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = tmem + lane_base + t * 256 + hf * 64;
@@ -430,6 +441,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
       tmem_ld32(tb + 32, rs + 32);
       tmem_ld32(tb + 128, rp);
       tmem_ld32(tb + 160, rp + 32);
+      if (it + 1 < n_items && i < S) lse_next = a.lse[(long long)(w + gridDim.x) * S + i];
       if (MODE == SVLA_ATTN_TRAJ_CAUSAL) named_bar_sync(1, 256);  // sTraj visible (overlaps the TMEM loads)
       tmem_wait_ld();
       // P in place of S (fp32); key columns >= S (zero-filled K / V rows) and masked pairs give exactly 0
@@ -477,10 +489,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
         }
       }
       // delta_i = sum over both column halves, in a fixed order
-      float* sd = sDelta + t * 256;
-      sd[hf * 128 + i] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-      named_bar_sync(2, 256);
-      const float delta = sd[i] + sd[128 + i];
+      const uint32_t sd = smem_u32(sDelta + t * 256);
+      sts_f32(sd + (hf * 128 + i) * 4, (d4[0] + d4[1]) + (d4[2] + d4[3]));
+      named_bar_sync(2 + (warp & 3), 64);  // only the two warps of this TMEM lane quadrant exchange their halves
+      const float delta = lds_f32(sd + i * 4) + lds_f32(sd + (128 + i) * 4);
       mbar_wait(pds_free, (it & 1) ^ 1);  // the previous item's gradient MMAs no longer read the P / dS tiles
 #pragma unroll
       for (int l8 = 0; l8 < 8; ++l8) {
@@ -502,8 +514,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_kernel(const __gri
           pw[e2] = *reinterpret_cast<const uint32_t*>(&hp);
           dw[e2] = *reinterpret_cast<const uint32_t*>(&hd);
         }
-        *reinterpret_cast<uint4*>(sP + off) = up;
-        *reinterpret_cast<uint4*>(sdS + off) = ud;
+        sts128(smem_u32(sP) + off, up);
+        sts128(smem_u32(sdS) + off, ud);
       }
       fence_async_smem();
       tc_fence_before();
@@ -697,12 +709,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_x3_kernel(const __
     const int hf = (warp - 4) >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float sl2 = a.scale * kLog2e;
+    // the row's log-sum-exp is requested one item ahead: loaded next to its use it put an L2 / DRAM round trip in
+    // front of every item (the accumulators are usually ready when this group gets to them)
+    float lse_next = (n_items > 0 && i < S) ? a.lse[(long long)blockIdx.x * S + i] : 0.f;  // item w: rows w * S ..
     for (int it = 0; it < n_items; ++it) {
       const int w = blockIdx.x + it * gridDim.x, b = w / H, h = w % H, t = it & 1;
       const long long row0 = (long long)b * S;
       const int* traj = sTraj + t * 128;
       if (MODE == SVLA_ATTN_TRAJ_CAUSAL && hf == 0) sTraj[t * 128 + i] = (i < S) ? (int)a.traj[row0 + i] : -1 - i;
-      const float lse2 = (i < S) ? a.lse[((long long)b * H + h) * S + i] * kLog2e : 0.f;
+      const float lse2 = lse_next * kLog2e;
       mbar_wait(&sdp_full[t], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tb = tmem + lane_base + t * 256 + hf * 64;
@@ -711,6 +726,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_x3_kernel(const __
       tmem_ld32(tb + 32, rs + 32);
       tmem_ld32(tb + 128, rp);
       tmem_ld32(tb + 160, rp + 32);
+      if (it + 1 < n_items && i < S) lse_next = a.lse[(long long)(w + gridDim.x) * S + i];
       if (MODE == SVLA_ATTN_TRAJ_CAUSAL) named_bar_sync(1, 256);
       tmem_wait_ld();
       float d4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -724,10 +740,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_ws_bwd_x3_kernel(const __
         rs[e] = __float_as_uint(p);
         d4[e & 3] = fmaf(p, __uint_as_float(rp[e]), d4[e & 3]);
       }
-      float* sd = sDelta + t * 256;
-      sd[hf * 128 + i] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-      named_bar_sync(2, 256);
-      const float delta = sd[i] + sd[128 + i];
+      const uint32_t sd = smem_u32(sDelta + t * 256);
+      sts_f32(sd + (hf * 128 + i) * 4, (d4[0] + d4[1]) + (d4[2] + d4[3]));
+      named_bar_sync(2 + (warp & 3), 64);  // only the two warps of this TMEM lane quadrant exchange their halves
+      const float delta = lds_f32(sd + i * 4) + lds_f32(sd + (128 + i) * 4);
       mbar_wait(pb_free, (it & 1) ^ 1);
 #pragma unroll
       for (int l8 = 0; l8 < 8; ++l8) {
