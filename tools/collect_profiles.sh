@@ -13,7 +13,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $PER --csv
 for t in gemm_fwd:svla_gemm_tc gemm_fwd_bits:svla_gemm_tc gemm_dgrad:svla_gemm_tc gemm_dgrad_bits:svla_gemm_tc \
          gemm_res:svla_gemm_tc gemm_wgrad:svla_gemm_tc gemm_x3:svla_gemm_tc attn:attn_ws_fwd attn:attn_ws_bwd \
          attn_x3:attn_ws_fwd attn_x3:attn_ws_bwd_x3 attn_drop:attn_ws_bwd split:split_concat \
-         gae:gae_march loss:ppo_lag adam:clip_adam ln:layernorm_bwd; do
+         gae:gae_march loss:ppo_lag adam:clip_adam ln:layernorm_bwd ln_fwd:layernorm_fwd attn_cls:attn_cls_fwd \
+         attn_cls:attn_cls_bwd vision:attn_flash_fwd; do
   tgt=${t%%:*}; k=${t##*:}
   ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $O/ncu_${R}_${tgt}_${k} \
       python tools/ncu_targets.py $tgt 4 > $O/ncu_${R}_${tgt}_${k}.log 2>&1

@@ -3,7 +3,7 @@
 captures (`ncu -k regex:<kernel> -s 2 -c 1 ... python tools/ncu_targets.py <target>`).
 
 targets: gae | loss | adam | ln | gemm_fwd | gemm_fwd_bits | gemm_dgrad | gemm_dgrad_mask | gemm_dgrad_bits | gemm_res |
-         gemm_wgrad | gemm_x3 | attn | attn_x3 | attn_drop | split
+         gemm_wgrad | gemm_x3 | attn | attn_x3 | attn_drop | split | ln_fwd | attn_cls | vision
 """
 from __future__ import annotations
 
@@ -115,6 +115,25 @@ def main():
         fn = lambda: (ops.attn_fwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, lse, B, S, **kw),  # noqa: E731
                       ops.attn_bwd(0, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, dqkv[:, :D],
                                    dqkv[:, D:2 * D], dqkv[:, 2 * D:], lse, B, S, **kw))
+    elif target == "ln_fwd":
+        R, D = 119808, 512
+        x, y = torch.randn(R, D, device=dev).to(bf), torch.empty(R, D, device=dev, dtype=bf)
+        g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+        mean, rstd = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        fn = lambda: ops.layernorm_fwd(x, g, b, y, mean=mean, rstd=rstd)  # noqa: E731
+    elif target == "attn_cls":  # CLS-row attention of the last fusion layer (one query per sequence and head)
+        B, S, D = 1024, 117, 512
+        kv = torch.randn(B * S, 2 * D, device=dev).to(bf) * 0.5
+        q0, o, do = [torch.randn(B, D, device=dev).to(bf) * 0.5 for _ in range(3)]
+        dq0, dkv = torch.empty_like(q0), torch.empty_like(kv)
+        lse = torch.empty(B * 8, device=dev)
+        fn = lambda: (ops.attn_cls_fwd(q0, kv[:, :D], kv[:, D:], o, lse, B, S),  # noqa: E731
+                      ops.attn_cls_bwd(q0, kv[:, :D], kv[:, D:], o, do, dq0, dkv[:, :D], dkv[:, D:], lse, B, S))
+    elif target == "vision":  # rollout-side DINOv2 ViT-S/14 preprocessor (attn_flash + K = 384 GEMMs), 256 frames
+        from safevla_b200.vision import B200DinoViTPreprocessor, init_hub_state_dict
+        pre = B200DinoViTPreprocessor("rgb", init_hub_state_dict(0), precision="bf16", device=dev)
+        fr = torch.randint(0, 256, (256, 224, 384, 3), dtype=torch.uint8, device=dev)
+        fn = lambda: pre.encode(fr)  # noqa: E731
     elif target == "split":
         x = torch.randn(119808, 512, device=dev)
         fn = lambda: ops.split_concat(x, 512, 119808, 512, 1, (0, 1, 0))  # noqa: E731
