@@ -809,7 +809,9 @@ def test_attention_split_operand_matches_fp64(dev, mode, S, B, adjacent):
         assert relerr(got, exp) < 3e-5, (name, relerr(got, exp))
 
 
-@pytest.mark.parametrize("M,N,K", [(512, 2048, 512), (117 * 70, 512, 384), (300, 256, 64), (4096 + 77, 2048, 512)])
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 512), (117 * 70, 512, 384), (300, 256, 64), (4096 + 77, 2048, 512),
+                                   (600, 576, 512),    # 18 record words per row: the 8-byte record path, ragged last tile
+                                   (1000, 640, 256)])  # 20 words: 16-byte records, last tile half empty
 def test_gemm_relu_bit_record_epilogues(dev, M, N, K):
     """RELU_BITS writes relu(x W^T + b) and one bit per element; MASK_BITS applies that record in the dgrad: both
     bit-identical to the RELU / RELU_MASK epilogues they replace (the record is 1/16 of the mask operand's bytes)."""
