@@ -11,6 +11,7 @@ config 2 (8 192 rows x 117 tokens) fits in HBM; the decoder (needs whole traject
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -83,6 +84,8 @@ class Tower:
         # parity-grade tensor-core mode: fp32 activations / weights, every tensor-core-shaped product evaluated as
         # 3 (or 6) split-bf16 products in one tcgen05 launch (ops.gemm split=); 0 = operands as they are
         self.split = split
+        # residual add of the attention sub-layer inside LayerNorm instead of the out-projection epilogue (encoder_fwd)
+        self.ln_res = os.environ.get("SVLA_LN_RES", "1") != "0"
 
     def _site(self, layer: int, kind: int, row0: int, row_stride: int = 1):
         """Dropout spec of site (tower, layer, kind): kind 0 attention probabilities, 1 dropout1, 2 FFN, 3 dropout2.
@@ -195,10 +198,13 @@ class Tower:
                 m1, r1 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
                 m2, r2 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
                 if not dp:
+                    # out-projection (K = N = 512): its epilogue with the residual operand runs at half the speed of the
+                    # plain one, LayerNorm streams the extra operand at 5.8 TB/s -- the residual add lives there
+                    # (self.ln_res; s1 then holds the sub-layer output WITHOUT the residual, as in the dropout branch)
                     s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
-                                       self._new(Ms, D), residual=x)
+                                       self._new(Ms, D), residual=None if self.ln_res else x)
                     x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Ms, D),
-                                           eps=LN_EPS, mean=m1, rstd=r1)
+                                           res=x if self.ln_res else None, eps=LN_EPS, mean=m1, rstd=r1)
                     hf, hfb = self._relu_fwd(x1, p + "linear1.weight", p + "linear1.bias", self._new(Ms, FF), keep=keep)
                     s2 = self._lin_fwd(hf, p + "linear2.weight", p + "linear2.bias", self._new(Ms, D), residual=x1)
                     x2 = ops.layernorm_fwd(s2, W.p(p + "norm2.weight"), W.p(p + "norm2.bias"), self._new(Ms, D),
@@ -310,7 +316,8 @@ class Tower:
             del dhf, ds2
             ds1 = ops.layernorm_bwd(dx1, t[f"s1_{l}"], W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), t[f"m1_{l}"],
                                     t[f"r1_{l}"], self._new(rows, D), W.g(p + "norm1.weight"), W.g(p + "norm1.bias"),
-                                    res=(t[f"xc_{l}"] if last else t[f"x_{l}"]) if dp else None)
+                                    res=(t[f"xc_{l}"] if last else t[f"x_{l}"]) if dp else
+                                    (t[f"x_{l}"] if (self.ln_res and not last) else None))
             del dx1
             dy1 = ops.dropout_rows(ds1, self._new(rows, D), site(1)) if dp else ds1
             dao = self._lin_bwd(dy1, t[f"ao_{l}"], p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias",
