@@ -192,6 +192,27 @@ class SafePPOValue(PPOValue):
     _cost = True
 
 
+class Imitation(AbstractActorCriticLoss):
+    """Expert-imitation plugin (customized_loss.py:17-83): binary cross-entropy between the policy's normalised logit of
+    ONE action (`distributions.logits[:, :, action_idx]`) and the expert observation `batch["observations"][uuid]`.
+    Not part of the PPO-Lagrangian update (the shipped pipeline never instantiates it); a [T, N] torch expression on the
+    tower output, whose gradient reaches the actor tower through the same autograd node the fused loss uses."""
+
+    def __init__(self, uuid: str = "expert_pickupable", action_idx: int = 8, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.uuid, self.action_idx = uuid, action_idx
+
+    def loss(self, step_count: int, batch: Dict, actor_critic_output, *args, **kwargs):
+        observations = batch["observations"]
+        if self.uuid not in observations:
+            raise NotImplementedError("Imitation loss requires either `expert_action` or `expert_policy`"
+                                      " sensor to be active.")
+        logit = actor_critic_output.distributions.logits[:, :, self.action_idx]
+        target = observations[self.uuid].to(device=logit.device, dtype=logit.dtype)
+        total = torch.nn.functional.binary_cross_entropy_with_logits(logit, target)
+        return total, {"expert_cross_entropy": total.item()}
+
+
 class _HLGaussFn(torch.autograd.Function):
     """One fused launch computes the loss and d loss / d logits; backward only scales by the upstream gradient."""
 

@@ -254,6 +254,39 @@ def test_loss_plugin_constructors_match_reference_signatures():
     SafePPOValue(clip_param=0.1, use_clipped_value_loss=False)
 
 
+def test_imitation_plugin_matches_reference_class():
+    """customized_loss.py:17-83 on the same logits / expert observation: the unmodified reference class (through the
+    shim, when the tree is present) and the closed form."""
+    from safevla_b200.losses import Imitation
+    from safevla_b200.misc import CategoricalDistr
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randn(5, 3, 12, generator=g, requires_grad=True)
+    expert = (torch.rand(5, 3, generator=g) < 0.4).float()
+
+    class Out:
+        distributions = CategoricalDistr(logits=raw)
+    batch = {"observations": {"expert_pickupable": expert}}
+    total, info = Imitation().loss(0, batch, Out)
+    x = torch.log_softmax(raw.detach(), -1)[:, :, 8]
+    closed = (torch.clamp(x, min=0) - x * expert + torch.log1p(torch.exp(-x.abs()))).mean()
+    assert abs(total.item() - closed.item()) < 1e-6 and abs(info["expert_cross_entropy"] - closed.item()) < 1e-6
+    total.backward()
+    assert raw.grad is not None and raw.grad.abs().sum() > 0
+    with pytest.raises(NotImplementedError):
+        Imitation(uuid="absent").loss(0, batch, Out)
+    from oracle import ref_shim
+    if ref_shim.reference_available():
+        ref_loss, _, _ = ref_shim.reference_modules()
+        raw2 = raw.detach().clone().requires_grad_(True)
+
+        class RefOut:
+            distributions = torch.distributions.Categorical(logits=raw2)
+        rt, rinfo = ref_loss.Imitation().loss(0, batch, RefOut)
+        rt.backward()
+        assert abs(rt.item() - total.item()) < 1e-6 and torch.allclose(raw2.grad, raw.grad, atol=1e-7)
+        assert set(rinfo) == set(info)
+
+
 def test_no_cpu_fallback():
     """Product entry points must fail loudly without a GPU instead of computing on the CPU."""
     if torch.cuda.is_available():
