@@ -260,15 +260,16 @@ int svla_attn_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const v
                   long long ldo, int dtype, float* lse, const int64_t* traj, const float* bias,
                   const int64_t* keymask, int B, int S, int H, int dh, float scale, svla_stream stream);
 /* the same with dropout on the attention probabilities (nn.MultiheadAttention dropout, applied after the softmax
- * normalisation): warp-specialised tcgen05 kernels only (bf16, S <= 128, modes FULL / TRAJ_CAUSAL); mask rows are
- * (b * H + h) * 128 + query, columns the keys. */
+ * normalisation): tcgen05 kernels only (bf16, S <= 256, mode FULL).  Mask rows are (b * H + h) * W + query with
+ * W = 128 for S <= 128 and W = 256 for 128 < S <= 256 (the two-camera fusion block), columns the keys.  The backward
+ * of the S > 128 kernels takes delta from dO . O and therefore needs the forward output o (ignored for S <= 128). */
 int svla_attn_drop_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
                        long long ldo, float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,
                        const svla_dropout* drop, svla_stream stream);
 int svla_attn_drop_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
-                       const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
-                       const int64_t* traj, int B, int S, int H, int dh, float scale, const svla_dropout* drop,
-                       svla_stream stream);
+                       const void* o, const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd,
+                       const float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,
+                       const svla_dropout* drop, svla_stream stream);
 int svla_attn_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
                   const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, int dtype,
                   const float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,

@@ -121,8 +121,8 @@ PROTOTYPES: Dict[str, list] = {
     "svla_dropout_rows": [c_p, c_p, C.c_int, c_ll, c_p, C.c_int, c_ll, c_ll, C.c_int, C.POINTER(Dropout), c_p],
     "svla_attn_drop_fwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_float, C.POINTER(Dropout), c_p],
-    "svla_attn_drop_bwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_ll, c_p, c_p, C.c_int, C.c_int,
-                           C.c_int, C.c_int, C.c_float, C.POINTER(Dropout), c_p],
+    "svla_attn_drop_bwd": [c_p, C.c_int, c_p, c_p, c_p, c_ll, c_p, c_p, c_ll, c_p, c_p, c_p, c_ll, c_p, c_p, C.c_int,
+                           C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(Dropout), c_p],
     "svla_split_concat": [c_p, c_p, c_ll, c_ll, C.c_int, c_p, c_ll, C.c_int, C.c_int, C.POINTER(C.c_int), c_p],
     "svla_hash_rows": [c_p, c_p, c_ll, C.c_int, c_p, c_p],
     "svla_episode_cost_step": [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p],

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bf
         float p = __expf(sc[i0 + i] - mx);
         sum += p;  // the normaliser is the undropped row sum
         if (DROP)  // mask row = the CLS row of this (sequence, head) in the full-sequence mask
-          p = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * 128u, (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
+          p = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * (S > 128 ? 256u : 128u), (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
         float vf[8];
         unpack8(vr[i], vf);
 #pragma unroll
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128, 4) attn_cls_bwd_bf16_kernel(
         const float p = __expf(s * scale - l_);
         float pm = p;  // P~ = P * keep / (1 - p_drop): delta = dO . O = rowsum(P~ dP) holds with O computed from P~
         if (drop.thr != 0u)
-          pm = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * 128u, (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
+          pm = ((dropout_keep8(drop, drop.row0 + (uint32_t)wid * (S > 128 ? 256u : 128u), (uint32_t)(j >> 3)) >> (j & 7)) & 1u) ? p * drop.scale : 0.f;
         const float dsj = fmaf(pm, dp, -p * delta);
         float a[8], bb[8];
 #pragma unroll
@@ -362,10 +362,11 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
   attn_cls_fwd_bf16_kernel<NQ_, DR_><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,    \
                                                            (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, lse, \
                                                            B, S, H, scale, da)
-    SVLA_CHECK_ARG(da.thr == 0u || S <= 128, "CLS-row attention with dropout: S <= 128 (the mask rows are 128 wide)");
-    if (da.thr != 0u) {
+    SVLA_CHECK_ARG(da.thr == 0u || S <= 256, "CLS-row attention with dropout: S <= 256");
+    if (da.thr != 0u) {  // mask row of sequence-head w: w * 128 (S <= 128) or w * 256, as in the full-sequence kernels
       if (S <= 64) SVLA_CLS_FWD(16, true);
-      else SVLA_CLS_FWD(32, true);
+      else if (S <= 128) SVLA_CLS_FWD(32, true);
+      else SVLA_CLS_FWD(64, true);
     } else if (S <= 64) SVLA_CLS_FWD(16, false);
     else if (S <= 128) SVLA_CLS_FWD(32, false);
     else SVLA_CLS_FWD(64, false);
@@ -392,7 +393,7 @@ extern "C" int svla_attn_cls_bwd(svla_ctx* ctx, const void* q, long long ldq, co
   const long long threads = (long long)B * H * 32;
   if (dtype == SVLA_BF16 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 && lddkv % 8 == 0 && al16(q) &&
       al16(k) && al16(v) && al16(o) && al16(d_o) && al16(dq) && al16(dk) && al16(dv)) {
-    SVLA_CHECK_ARG(da.thr == 0u || S <= 128, "CLS-row attention with dropout: S <= 128 (the mask rows are 128 wide)");
+    SVLA_CHECK_ARG(da.thr == 0u || S <= 256, "CLS-row attention with dropout: S <= 256");
     attn_cls_bwd_bf16_kernel<64><<<(unsigned)((threads + 127) / 128), 128, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (const __nv_bfloat16*)o,
         (const __nv_bfloat16*)d_o, ldo, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, lddkv, lse, B, S,

@@ -135,6 +135,11 @@ attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
           p[e] = ok ? exp2f(__uint_as_float(r[j8 * 8 + e]) * sl2 - mxs) : 0.f;
           sum += p[e];
         }
+        if (MODE == SVLA_ATTN_FULL && a.drop.thr != 0u) {  // the normaliser stays the undropped row sum
+          const uint32_t keep = dropout_keep8(a.drop, a.drop.row0 + (uint32_t)((b * a.H + h) * S2 + i), (uint32_t)(c * 4 + j8));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) p[e] = ((keep >> e) & 1u) ? p[e] * a.drop.scale : 0.f;
+        }
         store_p8(sP, tid, c * 4 + j8, p);
       }
     }
@@ -298,6 +303,17 @@ attn_tc2_bwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
               p[e] = ok ? exp2f(__uint_as_float(rs[j8 * 8 + e]) * sl2 - l2) : 0.f;
               ds[e] = ok ? p[e] * (__uint_as_float(rp[j8 * 8 + e]) - dl) : 0.f;
             }
+            if (MODE == SVLA_ATTN_FULL && a.drop.thr != 0u) {
+              // P~ = P keep / (1 - p) feeds dV; dS = P~ dP - P delta, delta = dO . O = rowsum(P~ dP) (O is the dropped output)
+              const uint32_t keep = dropout_keep8(a.drop, a.drop.row0 + (uint32_t)(w * S2 + gi),
+                                                  (uint32_t)(((j * TS + cb) >> 3) + j8));
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float pm = ((keep >> e) & 1u) ? p[e] * a.drop.scale : 0.f;
+                ds[e] = fmaf(pm, __uint_as_float(rp[j8 * 8 + e]), -p[e] * dl);  // p = 0 where masked: ds = 0 there
+                p[e] = pm;
+              }
+            }
             store_p8_sts(sP, qrow, (cb >> 3) + j8, p);
             store_p8_sts(sdS, qrow, (cb >> 3) + j8, ds);
           }
@@ -415,6 +431,14 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 }  // namespace
 
+int svla_attn_tc2_fwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                           long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                           const svla_dropout* drop, cudaStream_t st);
+int svla_attn_tc2_bwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                           const void* o, const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd,
+                           const float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                           const svla_dropout* drop, cudaStream_t st);
+
 bool svla_attn_tc2_supported(int mode, int dtype, int S, int dh, long long ld, long long ldo, const void* q,
                              const void* k, const void* v, const void* o) {
   return dtype == SVLA_BF16 && dh == DH && S > TS && S <= S2 &&
@@ -424,6 +448,12 @@ bool svla_attn_tc2_supported(int mode, int dtype, int S, int dh, long long ld, l
 
 int svla_attn_tc2_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
                       long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st) {
+  return svla_attn_tc2_fwd_drop(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, nullptr, st);
+}
+
+int svla_attn_tc2_fwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                           long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                           const svla_dropout* drop, cudaStream_t st) {
   CUtensorMap mq, mk, mv;
   const long long rows = (long long)B * S;
   int rc;
@@ -433,6 +463,7 @@ int svla_attn_tc2_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, con
   AttnTcArgs a{};
   a.mode = mode; a.B = B; a.S = S; a.H = H; a.scale = scale; a.traj = traj; a.lse = lse;
   a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo;
+  a.drop = make_drop_args(mode == SVLA_ATTN_FULL ? drop : nullptr);
   constexpr size_t smem = 98304 + 1024 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
@@ -453,6 +484,13 @@ int svla_attn_tc2_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, con
 int svla_attn_tc2_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, const void* o,
                       const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd, const float* lse,
                       const int64_t* traj, int B, int S, int H, float scale, cudaStream_t st) {
+  return svla_attn_tc2_bwd_drop(ctx, mode, q, k, v, ld, o, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale, nullptr, st);
+}
+
+int svla_attn_tc2_bwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                           const void* o, const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd,
+                           const float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                           const svla_dropout* drop, cudaStream_t st) {
   CUtensorMap mq, mk, mv, mdo;
   const long long rows = (long long)B * S;
   int rc;
@@ -465,6 +503,7 @@ int svla_attn_tc2_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, con
   a.o_in = reinterpret_cast<const __nv_bfloat16*>(o); a.d_o = reinterpret_cast<const __nv_bfloat16*>(d_o); a.ldo = ldo;
   a.dq = reinterpret_cast<__nv_bfloat16*>(dq); a.dk = reinterpret_cast<__nv_bfloat16*>(dk);
   a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.ldd = ldd;
+  a.drop = make_drop_args(mode == SVLA_ATTN_FULL ? drop : nullptr);
   constexpr size_t smem = 196608 + 1024 + 64 + 1024;
   static bool attr = false;
   if (!attr) {

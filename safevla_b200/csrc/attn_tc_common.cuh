@@ -56,6 +56,7 @@ struct AttnTcArgs {
   __nv_bfloat16* o; long long ldo;
   const __nv_bfloat16* o_in; const __nv_bfloat16* d_o;
   __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long ldd;
+  DropArgs drop;  // attn_tc2 (128 < S <= 256, mode FULL): dropout on P; mask row = row0 + item * 256 + query, group = key / 8
 };
 
 __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const uint32_t* r0, const uint32_t* r1, float mul) {

@@ -894,31 +894,52 @@ int svla_attn_ws_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, cons
   return attn_ws_bwd_impl(ctx, mode, q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale, nullptr, st);
 }
 
+// attn_tc2.cu: 128 < S <= 256 (the two-camera fusion block)
+bool svla_attn_tc2_supported(int mode, int dtype, int S, int dh, long long ld, long long ldo, const void* q,
+                             const void* k, const void* v, const void* o);
+int svla_attn_tc2_fwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld, void* o,
+                           long long ldo, float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                           const svla_dropout* drop, cudaStream_t st);
+int svla_attn_tc2_bwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
+                           const void* o, const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd,
+                           const float* lse, const int64_t* traj, int B, int S, int H, float scale,
+                           const svla_dropout* drop, cudaStream_t st);
+
 extern "C" int svla_attn_drop_fwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
                                   void* o, long long ldo, float* lse, const int64_t* traj, int B, int S, int H, int dh,
                                   float scale, const svla_dropout* drop, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && q && k && v && o, "NULL argument");
   SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
-  SVLA_CHECK_ARG(svla_attn_ws_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, o),
-                 "attention with dropout: bf16, S <= 128, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
+  const bool two_tile = S > TS && svla_attn_tc2_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, o);
+  SVLA_CHECK_ARG(two_tile || svla_attn_ws_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, o),
+                 "attention with dropout: bf16, S <= 256, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
   SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
   SVLA_CHECK_ARG(mode == SVLA_ATTN_FULL || !drop || drop->p == 0.f, "dropout exists for mode FULL (the fusion block) only");
   if (B <= 0) return SVLA_OK;
+  if (two_tile)
+    return svla_attn_tc2_fwd_drop(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, drop, as_stream(stream));
   return attn_ws_fwd_impl(ctx, mode, q, k, v, ld, o, ldo, lse, traj, B, S, H, scale, drop, as_stream(stream));
 }
 
 extern "C" int svla_attn_drop_bwd(svla_ctx* ctx, int mode, const void* q, const void* k, const void* v, long long ld,
-                                  const void* d_o, long long ldo, void* dq, void* dk, void* dv, long long ldd,
-                                  const float* lse, const int64_t* traj, int B, int S, int H, int dh, float scale,
-                                  const svla_dropout* drop, svla_stream stream) {
+                                  const void* o, const void* d_o, long long ldo, void* dq, void* dk, void* dv,
+                                  long long ldd, const float* lse, const int64_t* traj, int B, int S, int H, int dh,
+                                  float scale, const svla_dropout* drop, svla_stream stream) {
   SVLA_CHECK_ARG(ctx && q && k && v && d_o && dq && dk && dv && lse, "NULL argument");
   SVLA_CHECK_ARG(svla_dropout_ok(drop), "dropout p must be in [0, 1)");
-  SVLA_CHECK_ARG(svla_attn_ws_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, d_o) && ldd % 8 == 0 && al16(dq) &&
-                     al16(dk) && al16(dv),
-                 "attention with dropout: bf16, S <= 128, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
+  const bool two_tile = S > TS && svla_attn_tc2_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, d_o) &&
+                        ldd % 8 == 0 && al16(dq) && al16(dk) && al16(dv);
+  SVLA_CHECK_ARG(two_tile || (svla_attn_ws_supported(mode, SVLA_BF16, S, dh, ld, ldo, q, k, v, d_o) && ldd % 8 == 0 &&
+                              al16(dq) && al16(dk) && al16(dv)),
+                 "attention with dropout: bf16, S <= 256, head dim 64, FULL / TRAJ_CAUSAL, 16-byte aligned operands");
   SVLA_CHECK_ARG(mode != SVLA_ATTN_TRAJ_CAUSAL || traj, "TRAJ_CAUSAL needs traj");
   SVLA_CHECK_ARG(mode == SVLA_ATTN_FULL || !drop || drop->p == 0.f, "dropout exists for mode FULL (the fusion block) only");
   if (B <= 0) return SVLA_OK;
+  if (two_tile) {  // the two-tile kernel takes delta from dO . O: it needs the forward output
+    SVLA_CHECK_ARG(o && al16(o), "attention backward for 128 < S <= 256 needs the forward output o");
+    return svla_attn_tc2_bwd_drop(ctx, mode, q, k, v, ld, o, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale, drop,
+                                  as_stream(stream));
+  }
   return attn_ws_bwd_impl(ctx, mode, q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, lse, traj, B, S, H, scale, drop,
                           as_stream(stream));
 }

@@ -35,6 +35,10 @@ extern "C" int svla_gemm(svla_ctx* ctx, const svla_gemm_desc* d, svla_stream str
   SVLA_CHECK_ARG(!d->colsum_a || d->transA, "colsum_a needs transA (A stored [K, M])");
   if (d->M == 0 || d->N == 0) return SVLA_OK;
   const cudaStream_t st = as_stream(stream);
+  // validated above: the tensor-core path takes it.  (Not via svla_gemm_tc_supported(d) below -- that one applies the
+  // 16-byte row rule of a bf16 / fp32 mask operand to aux, which a record of N / 32 words need not meet; falling
+  // through to the CUDA-core kernel would silently drop the record.)
+  if (d->epilogue == SVLA_EPI_RELU_BITS || d->epilogue == SVLA_EPI_MASK_BITS) return svla_gemm_tc(ctx, d, st);
   if (d->colsum_a) {
     // bias gradient: produced by the tensor-core weight-gradient kernel itself when that path runs, else one extra pass
     if (d->impl != 1 && svla_gemm_tc_fuses_colsum(d)) return svla_gemm_tc(ctx, d, st);

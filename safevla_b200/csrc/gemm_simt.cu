@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmArgs g) {
 }  // namespace
 
 int svla_gemm_simt(svla_ctx* ctx, const svla_gemm_desc* d, cudaStream_t st) {
+  SVLA_CHECK_ARG(d->epilogue != SVLA_EPI_RELU_BITS && d->epilogue != SVLA_EPI_MASK_BITS,
+                 "the CUDA-core GEMM has no bit-record epilogue");
   GemmArgs g;
   g.d = *d;
   const int tiles = ((d->M + BM - 1) / BM) * ((d->N + BN - 1) / BN);

@@ -408,7 +408,7 @@ def attn_bwd(mode, q, k, v, o, d_o, dq, dk, dv, lse, B, S, H=8, dh=64, scale=0.1
     assert o.stride(0) == d_o.stride(0)
     if drop is not None:
         _timed("attn_bwd", 10.0 * B * H * S * S * dh, (mode, B, S, "bf16+drop"), lambda: check(
-            _lib().svla_attn_drop_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(d_o), d_o.stride(0),
+            _lib().svla_attn_drop_bwd(get_ctx(), mode, ptr(q), ptr(k), ptr(v), q.stride(0), ptr(o), ptr(d_o), d_o.stride(0),
                                       ptr(dq), ptr(dk), ptr(dv), dq.stride(0), ptr(lse), ptr(traj), B, S, H, dh, scale,
                                       C.byref(drop), stream_ptr()), "svla_attn_drop_bwd"))
         return

@@ -154,8 +154,8 @@ class Tower:
         Returns (cls [Rc, 512] adt, stash or None)."""
         W, adt = self.W, self.adt
         dp = self.drop_p > 0.0
-        if dp and (adt != torch.bfloat16 or 1 + TOK * self.C + L > 128):
-            raise NotImplementedError("dropout > 0 is built on the bf16 tensor-core kernels with S <= 128 (one camera)")
+        if dp and (adt != torch.bfloat16 or 1 + TOK * self.C + L > 256):
+            raise NotImplementedError("dropout > 0 is built on the bf16 tensor-core kernels (S <= 256)")
         Rc = vis[0].shape[0] // TOK
         S = 1 + TOK * self.C + L
         ve = "visual_encoder."
@@ -194,7 +194,7 @@ class Tower:
                 ao, lse = self._new(Ms, D), self._new(Rc * H * S, dtype=torch.float32)
                 ops.attn_fwd(ATTN_FULL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], ao, lse, Rc, S,
                              scale=1.0 / math.sqrt(DH), split=self.split,
-                             drop=self._site(l, 0, row_off * H * 128) if dp else None)
+                             drop=self._site(l, 0, row_off * H * (256 if S > 128 else 128)) if dp else None)
                 m1, r1 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
                 m2, r2 = self._new(Ms, dtype=torch.float32), self._new(Ms, dtype=torch.float32)
                 if not dp:
@@ -255,7 +255,7 @@ class Tower:
                     xcc = self._new(Rc, D)  # contiguous CLS rows: the LayerNorm residual operand has no row stride
                     ops.copy_rows(x, xcc, Rc, D, smap=RowMap(1, S, 0))
                     ops.attn_cls_fwd(q0, kv[:, 0:D], kv[:, D:2 * D], ao, lse, Rc, S, scale=1.0 / math.sqrt(DH),
-                                     drop=self._site(l, 0, row_off * H * 128))
+                                     drop=self._site(l, 0, row_off * H * (256 if S > 128 else 128)))
                     s1 = self._lin_fwd(ao, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", self._new(Rc, D))
                     ops.dropout_rows(s1, s1, crow(1))
                     x1 = ops.layernorm_fwd(s1, W.p(p + "norm1.weight"), W.p(p + "norm1.bias"), self._new(Rc, D),
@@ -331,7 +331,7 @@ class Tower:
                 dq0, dkv = self._new(Rc, D), self._new(Ms, 2 * D)
                 ops.attn_cls_bwd(q0, kv[:, 0:D], kv[:, D:2 * D], t[f"ao_{l}"], dao, dq0, dkv[:, 0:D], dkv[:, D:2 * D],
                                  t[f"lse_{l}"], Rc, S, scale=1.0 / math.sqrt(DH),
-                                 drop=self._site(l, 0, row_off * H * 128) if dp else None)
+                                 drop=self._site(l, 0, row_off * H * (256 if S > 128 else 128)) if dp else None)
                 xc = x.view(Rc, S * D)[:, :D]
                 # K/V projections of every token
                 self._gemm(dkv, x, gwi[D:3 * D], trans_a=True, trans_b=False, accumulate=True, colsum_a=gbi[D:3 * D])
@@ -347,7 +347,7 @@ class Tower:
                 ops.attn_bwd(ATTN_FULL, qkv[:, 0:D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], t[f"ao_{l}"], dao,
                              dqkv[:, 0:D], dqkv[:, D:2 * D], dqkv[:, 2 * D:3 * D], t[f"lse_{l}"], Rc, S,
                              scale=1.0 / math.sqrt(DH), split=self.split,
-                             drop=self._site(l, 0, row_off * H * 128) if dp else None)
+                             drop=self._site(l, 0, row_off * H * (256 if S > 128 else 128)) if dp else None)
                 dx = self._lin_bwd(dqkv, x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias",
                                    dx=self._new(Ms, D), residual=ds1)
                 del dqkv

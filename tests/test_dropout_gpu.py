@@ -118,20 +118,22 @@ def test_gemm_relu_bits_fused_dropout(dev, M, N, K):
     assert relerr(dz.float(), dz_ref) < 1e-2
 
 
-@pytest.mark.parametrize("S,B", [(117, 5), (128, 2), (33, 9)])
+@pytest.mark.parametrize("S,B", [(117, 5), (128, 2), (33, 9), (201, 3), (256, 2), (129, 2)])
 def test_attention_dropout_matches_torch_with_same_mask(dev, S, B):
-    """Dropout on the attention probabilities inside the warp-specialised kernels (forward and backward regenerate
-    the mask) against torch autograd with the dumped mask: O = (softmax(S) * M) V."""
+    """Dropout on the attention probabilities inside the tcgen05 kernels (forward and backward regenerate the mask)
+    against torch autograd with the dumped mask: O = (softmax(S) * M) V.  S <= 128: warp-specialised kernels, mask
+    rows 128 wide; 128 < S <= 256 (two-camera fusion block): the two-tile kernels, mask rows 256 wide."""
     from safevla_b200 import ops
     H, D, p = 8, 512, 0.1
     g = torch.Generator().manual_seed(S)
     qkv = (torch.randn(B * S, 3 * D, generator=g) * 0.6).to(dev, torch.bfloat16)
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     do = torch.randn(B * S, D, generator=g).to(dev, torch.bfloat16)
-    spec = ops.dropout_spec(p, 7, 1 * 64 + 0 * 8 + 0, 2, row0=3 * H * 128)
+    W = 128 if S <= 128 else 256  # mask rows per (sequence, head) and mask width
+    spec = ops.dropout_spec(p, 7, 1 * 64 + 0 * 8 + 0, 2, row0=3 * H * W)
     o, lse = torch.empty(B * S, D, device=dev, dtype=torch.bfloat16), torch.empty(B * H * S, device=dev)
     ops.attn_fwd(0, q, k, v, o, lse, B, S, drop=spec)
-    m = _mask(dev, B * H * 128, 128, p, 7, 64, 2, row0=3 * H * 128).view(B, H, 128, 128)[:, :, :S, :S]
+    m = _mask(dev, B * H * W, W, p, 7, 64, 2, row0=3 * H * W).view(B, H, W, W)[:, :, :S, :S]
     qr, kr, vr = [t.float().clone().requires_grad_(True) for t in (q, k, v)]
     sp = lambda t: t.view(B, S, H, 64).transpose(1, 2)  # noqa: E731
     P = torch.softmax(sp(qr) @ sp(kr).transpose(-1, -2) * 0.125, -1)
@@ -143,8 +145,9 @@ def test_attention_dropout_matches_torch_with_same_mask(dev, S, B):
     ref.backward(do.float())
     dqkv = torch.empty(B * S, 3 * D, device=dev, dtype=torch.bfloat16)
     ops.attn_bwd(0, q, k, v, o, do, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], lse, B, S, drop=spec)
+    tol = 3e-2 if S <= 128 else 6e-2  # the two-tile backward takes delta from the bf16 O . dO
     for name, got, exp in (("dq", dqkv[:, :D], qr.grad), ("dk", dqkv[:, D:2 * D], kr.grad), ("dv", dqkv[:, 2 * D:], vr.grad)):
-        assert relerr(got.float(), exp) < 3e-2, (name, relerr(got.float(), exp))
+        assert relerr(got.float(), exp) < tol, (name, relerr(got.float(), exp))
     # p = 0 through the dropout entry point == the plain kernel
     o0, o1 = torch.empty_like(o), torch.empty_like(o)
     ops.attn_fwd(0, q, k, v, o0, lse, B, S)
@@ -161,7 +164,8 @@ def _oracle_masks(dev, model, R, S, step):
         if key not in cache:
             site = TOWERS.index(prefix) * 64 + layer * 8 + kind
             if kind == 0:
-                m = _mask(dev, R * 8 * 128, 128, p, seed, site, step).view(R, 8, 128, 128)[:, :, :S, :S]
+                W = 128 if S <= 128 else 256
+                m = _mask(dev, R * 8 * W, W, p, seed, site, step).view(R, 8, W, W)[:, :, :S, :S]
             else:
                 m = _mask(dev, R * S, 2048 if kind == 2 else 512, p, seed, site, step).view(R, S, -1)
             cache[key] = m.cpu()
@@ -169,14 +173,15 @@ def _oracle_masks(dev, model, R, S, step):
     return drop
 
 
-@pytest.mark.parametrize("chunk_rows,budget", [(1024, 100 << 30), (6, 100 << 30), (4, 0)])
-def test_model_with_dropout_matches_oracle_given_the_masks(dev, chunk_rows, budget):
+@pytest.mark.parametrize("chunk_rows,budget,C", [(1024, 100 << 30, 1), (6, 100 << 30, 1), (4, 0, 1), (1024, 100 << 30, 2),
+                                                 (5, 0, 2)])
+def test_model_with_dropout_matches_oracle_given_the_masks(dev, chunk_rows, budget, C):
     """Whole three-tower forward + SafePPOLogGrad + backward with dropout 0.1 in every fusion layer (all four dropout
     positions of nn.TransformerEncoderLayer) against the CPU oracle evaluated with the very masks the device generated
     -- single chunk, row-chunked (masks addressed by global rows) and recompute-in-backward (masks regenerated)."""
     from safevla_b200.losses import SafePPOLogGrad
     from safevla_b200.model import B200SafeActorCritic
-    T, N, A, C = 6, 2, 6, 1
+    T, N, A = 6, 2, 6
     sd = init_state_dict(A, C, seed=17, actor_gain=1.0)
     ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.25, seed=3))
     obs = {k: v[:-1] for k, v in ro["observations"].items()}
@@ -186,7 +191,7 @@ def test_model_with_dropout_matches_oracle_given_the_masks(dev, chunk_rows, budg
     model.set_trainable_towers((0, 1))
     out, _ = model({k: v.to(dev) for k, v in obs.items()}, None, prev.to(dev), masks.to(dev))
     assert model.dropout_step == 1
-    drop = _oracle_masks(dev, model, T * N, 117, step=1)
+    drop = _oracle_masks(dev, model, T * N, 1 + 84 * C + 32, step=1)
     leaf = {k: (v.clone().requires_grad_(True) if "text_encoder" not in k and not k.endswith("div_term") else v)
             for k, v in sd.items()}
     ref = TO.safe_model_forward(leaf, obs, prev, masks, A, C, drop=drop)
@@ -228,8 +233,9 @@ def test_model_with_dropout_matches_oracle_given_the_masks(dev, chunk_rows, budg
     # measured (tools/dropout_grad_probe.py, 12 rows): norm errors <= 0.5 %, worst cosine 0.992 (linear1 of one layer)
     # -- the same as the bf16 path WITHOUT dropout shows on this tiny batch (0.994: operand rounding + ReLU-boundary
     # flips); a wrong mask or a missing 1 / (1 - p) anywhere would be a 10 % norm error or a cosine far below 0.9
-    assert worst[1] < 2e-2, worst
-    assert cos_min[1] > 0.985, cos_min
+    # two cameras (S = 201): the two-tile attention backward takes delta from the bf16 O . dO, its bound is wider
+    assert worst[1] < (2e-2 if C == 1 else 8e-2), worst
+    assert cos_min[1] > (0.985 if C == 1 else 0.97), cos_min
 
 
 def test_dropout_zero_is_the_parity_path_and_modes(dev):
@@ -259,14 +265,14 @@ def test_dropout_zero_is_the_parity_path_and_modes(dev):
         B200SafeActorCritic(A, C, precision="fp32", state_dict=sd, device=dev, dropout=0.1)
 
 
-@pytest.mark.parametrize("T,N", [(6, 2), (32, 8)])
-def test_cls_only_last_layer_under_dropout_equals_the_full_layer(dev, T, N):
+@pytest.mark.parametrize("T,N,C", [(6, 2, 1), (32, 8, 1), (6, 2, 2)])
+def test_cls_only_last_layer_under_dropout_equals_the_full_layer(dev, T, N, C):
     """The CLS-row shortcut of the last fusion layer (K/V for every token, everything else for row 0) addresses the
     full layer's masks (attention row h*128 of each sequence, sub-layer rows r*S): same outputs and gradients as
     running the full layer with the same seed.  (32, 8): 256 CLS rows, the fused bit-record FFN path; (6, 2): the
     small-chunk fallback (ReLU launch + row pass)."""
     from safevla_b200.model import B200SafeActorCritic
-    A, C = 6, 1
+    A = 6
     sd = init_state_dict(A, C, seed=17, actor_gain=1.0)
     ro = make_rollout(RolloutSpec(T, N, A, C, episode_end_prob=0.1, seed=3))
     obs = {k: v[:-1].to(dev) for k, v in ro["observations"].items()}
