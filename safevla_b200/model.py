@@ -10,7 +10,8 @@ Deliberate, documented differences from the reference (results identical with dr
     three towers (reference: per tower, per row, per forward -- SURVEY.md fact 6);
   * the last fusion layer only evaluates the CLS row it returns (fact 7);
   * heads that the separate-tower wrapper discards are not evaluated (fact 4);
-  * dropout is not applied (the parity setting; reference trains with p = 0.1, fact 8).
+  * dropout is off by default (the parity setting; the reference trains with p = 0.1, fact 8): `dropout=0.1` turns the
+    fusion block's four dropout sites on (counter-based masks, bf16 precision).
 """
 from __future__ import annotations
 
