@@ -186,8 +186,10 @@ __device__ __forceinline__ float rows4_sum(float v) {
   return v;
 }
 
-template <int NQ, bool DROP>  // key quads: S <= 4 * NQ; DROP: dropout on the probabilities (S <= 128 only)
-__global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
+// KB: quads (4 keys x 128 B) with loads in flight together per warp.  16 (8 KB per warp, three CTAs per SM) halves the
+// number of dependent DRAM round trips of an item against 8 (4 KB, four CTAs per SM).
+template <int NQ, bool DROP, int KB>  // key quads: S <= 4 * NQ; DROP: dropout on the probabilities
+__global__ void __launch_bounds__(128, KB == 16 ? 3 : 4) attn_cls_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
                                                                 const __nv_bfloat16* __restrict__ k,
                                                                 const __nv_bfloat16* __restrict__ v, long long ldkv,
                                                                 __nv_bfloat16* __restrict__ o, long long ldo,
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(128, 4) attn_cls_fwd_bf16_kernel(const __nv_bf
   unpack8(__ldg(reinterpret_cast<const uint4*>(q + (long long)b * ldq + h * DH + c * 8)), qv);
   const __nv_bfloat16* kb = k + (long long)b * S * ldkv + h * DH + c * 8;
   const __nv_bfloat16* vb = v + (long long)b * S * ldkv + h * DH + c * 8;
-  constexpr int kBatch = 8;  // quads with loads in flight together
+  constexpr int kBatch = KB;
   float sc[NQ];
   float mx = -INFINITY;
 #pragma unroll
@@ -359,7 +361,7 @@ extern "C" int svla_attn_cls_fwd(svla_ctx* ctx, const void* q, long long ldq, co
     const unsigned grid = (unsigned)((threads + 127) / 128);
     const auto st = as_stream(stream);
 #define SVLA_CLS_FWD(NQ_, DR_)                                                                                      \
-  attn_cls_fwd_bf16_kernel<NQ_, DR_><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,    \
+  attn_cls_fwd_bf16_kernel<NQ_, DR_, (NQ_ >= 32 && !(DR_)) ? 16 : 8><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,    \
                                                            (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, lse, \
                                                            B, S, H, scale, da)
     SVLA_CHECK_ARG(da.thr == 0u || S <= 256, "CLS-row attention with dropout: S <= 256");
