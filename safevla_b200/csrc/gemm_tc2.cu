@@ -293,6 +293,30 @@ __global__ void __launch_bounds__(256) tc2_splitk_reduce_kernel(TcArgs g) {
       g.asum[m] += v;
     }
   }
+  // weight gradients (every split launch of the towers): fp32 C, no bias / epilogue / residual -- four elements per
+  // thread and 16-byte accesses; the same split order per element as the scalar loop below, so identical bits
+  if (g.dtypeC == SVLA_F32 && !g.bias && g.epilogue == SVLA_EPI_NONE && !g.residual && (g.ldc & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) {
+    float* C = reinterpret_cast<float*>(g.C);
+    const long long total4 = total >> 2;  // N is a multiple of 64
+    for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < total4; i4 += (long long)gridDim.x * blockDim.x) {
+      const long long i = i4 << 2;
+      const int m = (int)(i / g.N), n = (int)(i % g.N);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < g.splits; ++s) {
+        const float4 p = __ldcs(reinterpret_cast<const float4*>(g.ws + (size_t)s * total + i));
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      v.x *= g.alpha; v.y *= g.alpha; v.z *= g.alpha; v.w *= g.alpha;
+      float4* c = reinterpret_cast<float4*>(C + (long long)m * g.ldc + n);
+      if (g.accumulate) {
+        const float4 o = *c;
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *c = v;
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / g.N), n = (int)(i % g.N);
     float v = 0.f;
