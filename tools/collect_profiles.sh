@@ -10,6 +10,11 @@ PER=$(python -c "import json,sys; print(json.loads(open('$O/bench_plain_$R.log')
 echo "skip $SKIP launches, capture $PER (one timed step)"
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $PER --csv --log-file $O/launches_$R.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-baseline > $O/bench_under_ncu_$R.log 2>&1
+if [ -n "$LAUNCHES_ONLY" ]; then  # refresh the launch list only (the ncu --set full captures take ~8 GPU-minutes)
+  python tools/ncu_summarize.py launches $O/launches_$R.csv $O/launches_$R.json > $O/launches_$R.txt 2>&1
+  gzip -f $O/launches_$R.csv
+  exit 0
+fi
 for t in gemm_fwd:svla_gemm_tc gemm_fwd_bits:svla_gemm_tc gemm_dgrad:svla_gemm_tc gemm_dgrad_bits:svla_gemm_tc \
          gemm_res:svla_gemm_tc gemm_wgrad:svla_gemm_tc gemm_x3:svla_gemm_tc attn:attn_ws_fwd attn:attn_ws_bwd \
          attn_x3:attn_ws_fwd attn_x3:attn_ws_bwd_x3 attn_drop:attn_ws_bwd split:split_concat \
