@@ -33,7 +33,7 @@ namespace {
 constexpr int S2 = 256;  // maximum sequence length of these kernels
 
 // ------------------------------------------------------------------------------------------ forward
-template <int MODE>
+template <int MODE, bool DROP>  // DROP: dropout on P (compiled out of the plain kernels: its presence alone cost 20 %)
 __global__ void __launch_bounds__(128)
 attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                     const __grid_constant__ CUtensorMap mv, AttnTcArgs a) {
@@ -135,7 +135,7 @@ attn_tc2_fwd_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
           p[e] = ok ? exp2f(__uint_as_float(r[j8 * 8 + e]) * sl2 - mxs) : 0.f;
           sum += p[e];
         }
-        if (MODE == SVLA_ATTN_FULL && a.drop.thr != 0u) {  // the normaliser stays the undropped row sum
+        if (DROP) {  // the normaliser stays the undropped row sum
           const uint32_t keep = dropout_keep8(a.drop, a.drop.row0 + (uint32_t)((b * a.H + h) * S2 + i), (uint32_t)(c * 4 + j8));
 #pragma unroll
           for (int e = 0; e < 8; ++e) p[e] = ((keep >> e) & 1u) ? p[e] * a.drop.scale : 0.f;
@@ -467,16 +467,19 @@ int svla_attn_tc2_fwd_drop(svla_ctx* ctx, int mode, const void* q, const void* k
   constexpr size_t smem = 98304 + 1024 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
-    SVLA_CUDA(cudaFuncSetAttribute(attn_tc2_fwd_kernel<SVLA_ATTN_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    SVLA_CUDA(cudaFuncSetAttribute(attn_tc2_fwd_kernel<SVLA_ATTN_TRAJ_CAUSAL>,
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc2_fwd_kernel<SVLA_ATTN_FULL, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc2_fwd_kernel<SVLA_ATTN_FULL, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVLA_CUDA(cudaFuncSetAttribute(attn_tc2_fwd_kernel<SVLA_ATTN_TRAJ_CAUSAL, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   const long long items = (long long)B * H * ((S + TS - 1) / TS);
   const int grid = (int)std::min<long long>(items, 2LL * ctx->sm_count);
-  if (mode == SVLA_ATTN_FULL) attn_tc2_fwd_kernel<SVLA_ATTN_FULL><<<grid, 128, smem, st>>>(mq, mk, mv, a);
-  else attn_tc2_fwd_kernel<SVLA_ATTN_TRAJ_CAUSAL><<<grid, 128, smem, st>>>(mq, mk, mv, a);
+  if (mode == SVLA_ATTN_FULL && a.drop.thr != 0u) attn_tc2_fwd_kernel<SVLA_ATTN_FULL, true><<<grid, 128, smem, st>>>(mq, mk, mv, a);
+  else if (mode == SVLA_ATTN_FULL) attn_tc2_fwd_kernel<SVLA_ATTN_FULL, false><<<grid, 128, smem, st>>>(mq, mk, mv, a);
+  else attn_tc2_fwd_kernel<SVLA_ATTN_TRAJ_CAUSAL, false><<<grid, 128, smem, st>>>(mq, mk, mv, a);
   SVLA_LAUNCH_CHECK();
   return SVLA_OK;
 }
